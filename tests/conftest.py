@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+
+
+@pytest.fixture(scope="session")
+def orc():
+    from oracle.okd import Oracle, build
+
+    build()
+    return Oracle()
+
+
+@pytest.fixture(scope="session")
+def orc32():
+    from oracle.okd import Oracle, build
+
+    build()
+    return Oracle(leaf_cap=32)
