@@ -163,8 +163,8 @@ def test_faithful_and_canonical_agree_on_order_independent_fields(orc, n):
     assert _tree_sets(a) == _tree_sets(b) == _tree_sets(c)
     ia = a["is_internal"].astype(bool)
     for other in (b, c):
-        assert np.allclose(other["m"][ia], a["m"][ia], rtol=1e-12, atol=0)          # tolerance: summation order only (reference self-noise)
-        assert np.allclose(other["cm"][ia], a["cm"][ia], rtol=0, atol=1e-13)
+        assert np.allclose(other["m"][ia], a["m"][ia], rtol=1e-11, atol=0)          # tolerance: summation order only (reference self-noise ~ n*eps)
+        assert np.allclose(other["cm"][ia], a["cm"][ia], rtol=0, atol=1e-11)
     # dense layouts: same nodes, preorder numbering
     d, _, last_d = orc.build_tree(parts, seed=3)
     e, _, last_e = orc.build_tree_canonical(parts, layout=LAYOUT_DENSE)
