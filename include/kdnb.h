@@ -1,0 +1,148 @@
+/*
+ * kdnb.h — C ABI of libkdnb.so: the kD-tree N-body step of MarkCLewis/MultiLanguageKDTree
+ * (Parallel/RustVersion) on NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for ONE path of the reference: `simple_sim` and the three stages it
+ * calls (tree build, theta-criterion walk, kick/drift).  The reference has no FFI of its own
+ * (SURVEY.md §8b); every entry point below cites the Rust item it replaces, relative to
+ * /root/reference/Parallel/RustVersion/src/.  INTEGRATION.md shows the Rust `extern "C"` block and the
+ * patched `simple_sim` a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success or a negative KDNB_E_* code
+ * and never aborts the host process (the reference panics instead); the message is available from
+ * kdnb_last_error().  There is NO CPU fallback: without a CUDA device kdnb_create() fails.
+ * One context drives one GPU from one host thread; multi-GPU = one process/context per GPU joined with
+ * kdnb_comm_init().
+ */
+#ifndef KDNB_H
+#define KDNB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KDNB_VERSION 100
+
+enum {
+  KDNB_OK = 0,
+  KDNB_E_INVALID = -1,  /* bad argument / call order */
+  KDNB_E_CUDA = -2,     /* CUDA runtime error (message in kdnb_last_error) */
+  KDNB_E_NOMEM = -3,    /* device or host allocation failed */
+  KDNB_E_NCCL = -4,     /* NCCL error or libnccl not loadable */
+  KDNB_E_CAPACITY = -5  /* caller buffer too small */
+};
+
+/* mirrors `pub struct Particle` (array_particle.rs:3-8): same field order, 64 bytes */
+typedef struct kdnb_particle {
+  double p[3];
+  double v[3];
+  double r;
+  double m;
+} kdnb_particle;
+
+enum { KDNB_LEAF = 0, KDNB_INTERNAL = 1 };
+#define KDNB_NO_INDEX UINT64_MAX /* usize::MAX of NEGS (array_kd_tree.rs:16) */
+
+/* mirrors `pub enum KDTree` (array_kd_tree.rs:18-34) as a flat record.
+ *   Leaf     { num_parts, leaf_parts }  -> kind=KDNB_LEAF, num_parts, leaf_parts = indices[leaf_first .. leaf_first+num_parts)
+ *   Internal { split_dim, split_val, m, cm, size, left, right } -> kind=KDNB_INTERNAL and those fields
+ * A slot the build never wrote (the padded layout leaves about half of them) is the reference's default
+ * Leaf{0, NEGS}: kind=KDNB_LEAF, num_parts=0, leaf_first=KDNB_NO_INDEX. */
+typedef struct kdnb_node {
+  uint32_t kind;
+  uint32_t split_dim;
+  uint64_t num_parts;
+  uint64_t leaf_first;
+  double split_val;
+  double m;
+  double cm[3];
+  double size;
+  uint64_t left;
+  uint64_t right;
+} kdnb_node;
+
+enum {
+  KDNB_LAYOUT_PADDED = 0, /* build_tree_par4 (array_kd_tree.rs:515-583): right = cur+1+nodes_needed(left_len) */
+  KDNB_LAYOUT_DENSE = 1   /* build_tree (array_kd_tree.rs:63-130): right = last node of left subtree + 1 */
+};
+
+enum {
+  KDNB_FLAG_PROFILE = 1u,     /* record CUDA events around build / walk / kick / exchange */
+  KDNB_FLAG_WALK_COUNTS = 2u, /* walk also counts node tests / accepts / leaf visits / pair interactions per particle */
+  KDNB_FLAG_EXACT_MATH = 4u   /* force magnitudes with IEEE sqrt and divide exactly as the reference writes them
+                                 (default: rsqrt-based, <= 2 ulp apart; acceptance tests are always exact) */
+};
+
+typedef struct kdnb_config {
+  uint32_t struct_size; /* = sizeof(kdnb_config) */
+  int32_t device;       /* CUDA device ordinal */
+  uint32_t max_parts;   /* MAX_PARTS (array_kd_tree.rs:14), 4..32; 0 -> 8 */
+  int32_t layout;       /* KDNB_LAYOUT_* */
+  double theta;         /* THETA (array_kd_tree.rs:15); 0 -> 0.3 */
+  uint32_t flags;       /* KDNB_FLAG_* */
+  uint32_t reserved;
+} kdnb_config;
+
+typedef struct kdnb_ctx kdnb_ctx;
+
+/* ---- lifetime: the prologue of simple_sim (array_kd_tree.rs:624-630) owns acc / tree / indices; here the context does */
+kdnb_ctx* kdnb_create(const kdnb_config* cfg); /* NULL on failure: see kdnb_last_error(NULL) */
+void kdnb_destroy(kdnb_ctx* ctx);
+const char* kdnb_last_error(const kdnb_ctx* ctx); /* ctx may be NULL (creation errors) */
+int kdnb_version(void);
+
+/* ---- state: `bodies: &mut Vec<Particle>` (array_kd_tree.rs:623).  AoS in, AoS out, original order kept */
+int kdnb_upload_particles(kdnb_ctx* ctx, const kdnb_particle* aos, uint64_t count);
+int kdnb_download_particles(kdnb_ctx* ctx, kdnb_particle* out, uint64_t capacity);
+uint64_t kdnb_particle_count(const kdnb_ctx* ctx);
+
+/* ---- the three stages of one step */
+int kdnb_build_tree(kdnb_ctx* ctx);             /* indices reset + build_tree_par4 / build_tree (array_kd_tree.rs:641-643) */
+int kdnb_calc_accel(kdnb_ctx* ctx);             /* acc[i] = calc_accel(i, bodies, tree) for all i (array_kd_tree.rs:647, :585-621) */
+int kdnb_kick_drift(kdnb_ctx* ctx, double dt);  /* v += dt*a; p += dt*v; a = 0 (array_kd_tree.rs:649-662) */
+
+/* ---- the driver: simple_sim(bodies, dt, steps) (array_kd_tree.rs:623-664) */
+int kdnb_simple_sim(kdnb_ctx* ctx, double dt, int64_t steps); /* on the uploaded state; asynchronous until a download / kdnb_synchronize */
+/* one-call drop-in with host buffers: upload, `steps` steps, download into `bodies` */
+int kdnb_simple_sim_host(const kdnb_config* cfg, kdnb_particle* bodies, uint64_t count, double dt, int64_t steps);
+/* the same on an existing context (buffers are reused across calls): upload + `steps` steps + download */
+int kdnb_simple_sim_bodies(kdnb_ctx* ctx, kdnb_particle* bodies, uint64_t count, double dt, int64_t steps);
+int kdnb_synchronize(kdnb_ctx* ctx);
+
+/* ---- results of the stages (parity hooks) */
+int kdnb_download_accel(kdnb_ctx* ctx, double* acc /* count*3, original particle order */);
+int kdnb_upload_accel(kdnb_ctx* ctx, const double* acc /* count*3, original order; test hook for kick_drift */);
+/* `tree: Vec<KDTree>` + `indices` after the build.  nodes: capacity `cap` records, receives kdnb_node_count();
+ * indices: count entries (tree order), may be NULL.  Node index positions are exactly the reference layout's. */
+int kdnb_download_tree(kdnb_ctx* ctx, kdnb_node* nodes, uint64_t cap, uint64_t* n_nodes, uint64_t* indices);
+/* per particle {internal nodes tested, monopoles accepted, leaves visited, pair interactions}; needs KDNB_FLAG_WALK_COUNTS */
+int kdnb_download_walk_counts(kdnb_ctx* ctx, uint64_t* counts /* count*4, original order */);
+
+/* ---- pure functions */
+uint64_t kdnb_nodes_needed(uint64_t num_parts, uint32_t max_parts); /* nodes_needed_for_particles (array_kd_tree.rs:45-53) */
+uint64_t kdnb_node_count(const kdnb_ctx* ctx); /* allocate_node_vec(count).len() for this context's layout (array_kd_tree.rs:55-60) */
+
+/* ---- multi-GPU (new; the reference is single-process).  Tree replicated, walk sharded by tree-ordered
+ * ranges, tree-ordered accelerations exchanged with one ncclAllGather per step. */
+int kdnb_comm_unique_id(void* id_out_128_bytes);
+int kdnb_comm_init(kdnb_ctx* ctx, const void* id_128_bytes, int rank, int world_size);
+
+/* ---- measurement */
+enum { KDNB_STAGE_BUILD = 0, KDNB_STAGE_WALK = 1, KDNB_STAGE_KICK = 2, KDNB_STAGE_EXCHANGE = 3, KDNB_STAGE_COUNT = 4 };
+int kdnb_stage_ms(kdnb_ctx* ctx, double ms_out[KDNB_STAGE_COUNT], uint64_t* steps_out); /* sums since last reset; needs KDNB_FLAG_PROFILE; synchronizes */
+int kdnb_stage_reset(kdnb_ctx* ctx);
+uint64_t kdnb_launch_count(const kdnb_ctx* ctx);     /* kernels launched by this context so far */
+int kdnb_measure_fp64_peak(kdnb_ctx* ctx, double* tflops_out); /* DFMA-chain microbenchmark: the walk's roofline denominator */
+int kdnb_flush_l2(kdnb_ctx* ctx);                     /* overwrite a 256 MiB scratch buffer */
+int kdnb_device_ms(kdnb_ctx* ctx, int begin_or_end, double* ms_out); /* CUDA-event stopwatch on the context's stream */
+
+/* page-locked host buffers for the transfers above (optional; any host pointer works, pinned is faster) */
+void* kdnb_host_alloc(uint64_t bytes);
+void kdnb_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KDNB_H */

@@ -1,0 +1,597 @@
+// build.cu — level-synchronous kD-tree build reproducing build_tree_par4 / build_tree
+// (Parallel/RustVersion/src/array_kd_tree.rs:515-583 and :63-130) node for node.
+//
+// Input: the three per-dimension sorted id lists from sort.cu.  Invariant kept at every level: inside each
+// node's slot range [a, a+len) every list holds exactly that node's particles, sorted by its dimension
+// (ties by ascending id).  Then for a node
+//   bbox[d]   = coordinates of the first / last entry of list d        (array_kd_tree.rs:532-547, min/max part)
+//   split_dim = widest extent, strict '>' so ties keep the lower dim    (:551-556)
+//   size      = extent along split_dim                                  (:557)
+//   mid       = a + len/2, split_val = coordinate of list[split_dim][mid] (:560-563)
+// and the children are obtained by a STABLE partition of the other two lists by "is in the left half of
+// list[split_dim]" — no selection passes, no reductions.
+//
+//  * levels whose segments are larger than BOT_CAP run as global kernels (stats, flags, count, scan, scatter);
+//  * once segments fit (<= BOT_CAP slots) ONE kernel finishes all remaining levels in shared memory, emits the
+//    leaves, the tree-ordered particle copies and sums m / sum(m*p) bottom-up inside the segment;
+//  * a last single-CTA kernel carries m / sum(m*p) up the few global levels.
+// m and cm are summed in the canonical order (leaf: ascending id, internal: left + right), see DESIGN.md.
+#include "ctx.cuh"
+
+namespace kdnb {
+
+struct Lists {
+  uint32_t* l[3];
+};
+struct Pos3c {
+  const double* p[3];
+};
+
+// ------------------------------------------------------------------------------------------ global levels
+
+__global__ void build_root(uint32_t* tstart, uint32_t* tlen, uint32_t* tnode, uint32_t n) {
+  tstart[0] = 0;
+  tlen[0] = n;
+  tnode[0] = 0;
+}
+
+__global__ void __launch_bounds__(128) level_stats(Pos3c pos, Lists L, int level, uint32_t mp, int layout,
+                                                   uint32_t* __restrict__ tstart, uint32_t* __restrict__ tlen,
+                                                   uint32_t* __restrict__ tnode, uint32_t* __restrict__ tmid,
+                                                   uint8_t* __restrict__ tsd, WNode* __restrict__ nodes) {
+  const uint32_t nseg = 1u << level;
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  const uint32_t off = nseg - 1;
+  const uint32_t a = tstart[off + s], len = tlen[off + s], node = tnode[off + s];
+  double mn[3], mx[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    mn[d] = pos.p[d][L.l[d][a]];
+    mx[d] = pos.p[d][L.l[d][a + len - 1]];
+  }
+  int sd = 0;
+  double ext = mx[0] - mn[0];
+#pragma unroll
+  for (int d = 1; d < 3; ++d) {
+    double e = mx[d] - mn[d];
+    if (e > ext) {
+      ext = e;
+      sd = d;
+    }
+  }
+  const uint32_t half = len / 2, mid = a + half;
+  const double split_val = pos.p[sd][L.l[sd][mid]];
+  const uint32_t nleft = (uint32_t)subtree_nodes(half, mp, layout);
+  WNode* nd = &nodes[node];
+  nd->size2 = __dmul_rn(ext, ext);
+  nd->size = ext;
+  nd->split_val = split_val;
+  nd->a = node + 1 + nleft;
+  nd->b = WN_INTERNAL | (uint32_t)sd;
+  tsd[off + s] = (uint8_t)sd;
+  tmid[off + s] = mid;
+  const uint32_t coff = 2 * nseg - 1;
+  tstart[coff + 2 * s] = a;
+  tlen[coff + 2 * s] = half;
+  tnode[coff + 2 * s] = node + 1;
+  tstart[coff + 2 * s + 1] = mid;
+  tlen[coff + 2 * s + 1] = len - half;
+  tnode[coff + 2 * s + 1] = node + 1 + nleft;
+}
+
+// side[id] = 0 if the particle falls in the left half of its node's split-dimension list, else 1
+__global__ void __launch_bounds__(LVL_THREADS) level_flags(Lists L, int level, uint32_t cps,
+                                                           const uint32_t* __restrict__ tstart,
+                                                           const uint32_t* __restrict__ tlen,
+                                                           const uint32_t* __restrict__ tmid,
+                                                           const uint8_t* __restrict__ tsd,
+                                                           uint8_t* __restrict__ side) {
+  const uint32_t seg = blockIdx.x / cps, chunk = blockIdx.x % cps;
+  const uint32_t off = (1u << level) - 1;
+  const uint32_t a = tstart[off + seg], len = tlen[off + seg], mid = tmid[off + seg];
+  const uint32_t* lst = L.l[tsd[off + seg]];
+#pragma unroll
+  for (int k = 0; k < LVL_CHUNK / LVL_THREADS; ++k) {
+    uint32_t o = chunk * LVL_CHUNK + k * LVL_THREADS + threadIdx.x;
+    if (o < len) side[lst[a + o]] = (a + o >= mid) ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(LVL_THREADS) level_count(Lists L, int level, uint32_t cps,
+                                                           const uint32_t* __restrict__ tstart,
+                                                           const uint32_t* __restrict__ tlen,
+                                                           const uint8_t* __restrict__ tsd,
+                                                           const uint8_t* __restrict__ side,
+                                                           uint32_t* __restrict__ cnt) {
+  __shared__ uint32_t wsum[LVL_THREADS / 32];
+  const uint32_t seg = blockIdx.x / cps, chunk = blockIdx.x % cps, e = blockIdx.y;
+  const uint32_t nseg = 1u << level, off = nseg - 1;
+  if (tsd[off + seg] == e) return;  // the split-dimension list is already partitioned
+  const uint32_t a = tstart[off + seg], len = tlen[off + seg];
+  const uint32_t* lst = L.l[e];
+  uint32_t c = 0;
+#pragma unroll
+  for (int k = 0; k < LVL_CHUNK / LVL_THREADS; ++k) {
+    uint32_t o = chunk * LVL_CHUNK + k * LVL_THREADS + threadIdx.x;
+    if (o < len) c += (side[lst[a + o]] == 0);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int k = 0; k < LVL_THREADS / 32; ++k) t += wsum[k];
+    cnt[((uint64_t)e * nseg + seg) * cps + chunk] = t;
+  }
+}
+
+// exclusive scan of each (list, segment) row of chunk counts
+__global__ void __launch_bounds__(256) level_scan(int level, uint32_t cps, const uint8_t* __restrict__ tsd,
+                                                  uint32_t* __restrict__ cnt) {
+  __shared__ uint32_t wsum[8];
+  const uint32_t seg = blockIdx.x, e = blockIdx.y;
+  const uint32_t nseg = 1u << level, off = nseg - 1;
+  if (tsd[off + seg] == e) return;
+  uint32_t* row = cnt + ((uint64_t)e * nseg + seg) * cps;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < cps; base += 256) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < cps ? row[i] : 0u, x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    uint32_t wp = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      uint32_t t = wsum[k];
+      if (k < w) wp += t;
+      total += t;
+    }
+    if (i < cps) row[i] = carry + wp + x - v;
+    carry += total;
+    __syncthreads();
+  }
+}
+
+// stable partition of list e inside each segment (copy for the split-dimension list)
+__global__ void __launch_bounds__(LVL_THREADS) level_scatter(Lists Lin, Lists Lout, int level, uint32_t cps,
+                                                             const uint32_t* __restrict__ tstart,
+                                                             const uint32_t* __restrict__ tlen,
+                                                             const uint32_t* __restrict__ tmid,
+                                                             const uint8_t* __restrict__ tsd,
+                                                             const uint8_t* __restrict__ side,
+                                                             const uint32_t* __restrict__ cnt) {
+  constexpr int IPT = LVL_CHUNK / LVL_THREADS;  // 8
+  __shared__ uint32_t wtot[LVL_THREADS / 32];
+  const uint32_t seg = blockIdx.x / cps, chunk = blockIdx.x % cps, e = blockIdx.y;
+  const uint32_t nseg = 1u << level, off = nseg - 1;
+  const uint32_t a = tstart[off + seg], len = tlen[off + seg], mid = tmid[off + seg];
+  const uint32_t* lin = Lin.l[e];
+  uint32_t* lout = Lout.l[e];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t wbase_off = chunk * LVL_CHUNK + w * (32 * IPT);
+
+  if (tsd[off + seg] == e) {
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      uint32_t o = wbase_off + k * 32 + lane;
+      if (o < len) lout[a + o] = lin[a + o];
+    }
+    return;
+  }
+  uint32_t id[IPT], bl[IPT];
+  uint32_t wl = 0;
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    uint32_t o = wbase_off + k * 32 + lane;
+    bool valid = o < len;
+    id[k] = valid ? lin[a + o] : 0u;
+    bool isleft = valid && (side[id[k]] == 0);
+    bl[k] = __ballot_sync(0xffffffffu, isleft);
+    wl += __popc(bl[k]);
+  }
+  if (lane == 0) wtot[w] = wl;
+  __syncthreads();
+  uint32_t wbase = 0;
+#pragma unroll
+  for (int k = 0; k < LVL_THREADS / 32; ++k)
+    if (k < w) wbase += wtot[k];
+  const uint32_t leftbase = cnt[((uint64_t)e * nseg + seg) * cps + chunk];  // lefts in earlier chunks of the segment
+  uint32_t pre = wbase;
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    uint32_t o = wbase_off + k * 32 + lane;
+    if (o < len) {
+      uint32_t lrank = leftbase + pre + __popc(bl[k] & lt);  // lefts before me in the segment
+      bool isleft = (bl[k] >> lane) & 1u;
+      uint32_t dst = isleft ? a + lrank : mid + (o - lrank);
+      lout[dst] = id[k];
+    }
+    pre += __popc(bl[k]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ bottom levels
+
+struct __align__(4) BotTab {
+  uint16_t a, len, mid;
+  uint8_t sd, kind;  // kind: 0 split, 1 leaf, 2 absent
+  uint32_t node;
+};
+static_assert(sizeof(BotTab) == 12, "BotTab");
+
+constexpr int BOT_THREADS = 512;
+constexpr int BOT_IPT = BOT_CAP / BOT_THREADS;  // 4
+constexpr int BOT_HEAP = 2048;
+constexpr int BOT_WARPS = BOT_THREADS / 32;
+
+struct BotSmem {
+  uint32_t gid[BOT_CAP];
+  uint16_t lst[2][3][BOT_CAP];
+  uint16_t segh[BOT_CAP];
+  uint16_t scan[BOT_CAP];
+  uint8_t side[BOT_CAP];
+  BotTab tab[BOT_HEAP];
+  uint32_t wtot[BOT_WARPS];
+  int flag;
+};
+
+__global__ void __launch_bounds__(BOT_THREADS)
+build_bottom(Pos3c pos, const double* __restrict__ mass, Lists L, int level, uint32_t mp, int layout,
+             const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ tlen,
+             const uint32_t* __restrict__ tnode, uint32_t* __restrict__ inv, WNode* __restrict__ nodes,
+             double4* __restrict__ ms, uint32_t* __restrict__ perm, uint32_t* __restrict__ rank,
+             PosM* __restrict__ posm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BotSmem& S = *reinterpret_cast<BotSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t off = (1u << level) - 1;
+  const uint32_t a0 = tstart[off + blockIdx.x], len0 = tlen[off + blockIdx.x], node0 = tnode[off + blockIdx.x];
+
+  // ---- load: local slot j <-> id of the j-th entry of the x list
+  for (uint32_t j = tid; j < len0; j += BOT_THREADS) {
+    uint32_t g = L.l[0][a0 + j];
+    S.gid[j] = g;
+    inv[g] = j;
+    S.lst[0][0][j] = (uint16_t)j;
+    S.segh[j] = 1;
+  }
+  if (tid == 0) {
+    BotTab t;
+    t.a = 0;
+    t.len = (uint16_t)len0;
+    t.mid = 0;
+    t.sd = 0;
+    t.kind = 0;
+    t.node = node0;
+    S.tab[1] = t;
+  }
+  __syncthreads();
+  for (uint32_t j = tid; j < len0; j += BOT_THREADS) {
+    S.lst[0][1][j] = (uint16_t)inv[L.l[1][a0 + j]];
+    S.lst[0][2][j] = (uint16_t)inv[L.l[2][a0 + j]];
+  }
+  __syncthreads();
+
+  int cur = 0, depth = 0;
+  for (int lev = 0;; ++lev) {
+    const uint32_t nn = 1u << lev;
+    if (tid == 0) S.flag = 0;
+    __syncthreads();
+    // ---- node statistics for this local level
+    for (uint32_t h = nn + tid; h < 2 * nn; h += BOT_THREADS) {
+      BotTab t = S.tab[h];
+      if (t.kind == 2) {
+        if (2 * h + 1 < BOT_HEAP) S.tab[2 * h].kind = S.tab[2 * h + 1].kind = 2;
+        continue;
+      }
+      if (t.len <= mp) {
+        S.tab[h].kind = 1;
+        if (2 * h + 1 < BOT_HEAP) S.tab[2 * h].kind = S.tab[2 * h + 1].kind = 2;
+        continue;
+      }
+      double mn[3], mx[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        mn[d] = pos.p[d][S.gid[S.lst[cur][d][t.a]]];
+        mx[d] = pos.p[d][S.gid[S.lst[cur][d][t.a + t.len - 1]]];
+      }
+      int sd = 0;
+      double ext = mx[0] - mn[0];
+#pragma unroll
+      for (int d = 1; d < 3; ++d) {
+        double e = mx[d] - mn[d];
+        if (e > ext) {
+          ext = e;
+          sd = d;
+        }
+      }
+      const uint32_t half = t.len / 2, mid = t.a + half;
+      const double split_val = pos.p[sd][S.gid[S.lst[cur][sd][mid]]];
+      const uint32_t nleft = (uint32_t)subtree_nodes(half, mp, layout);
+      WNode* nd = &nodes[t.node];
+      nd->size2 = __dmul_rn(ext, ext);
+      nd->size = ext;
+      nd->split_val = split_val;
+      nd->a = t.node + 1 + nleft;
+      nd->b = WN_INTERNAL | (uint32_t)sd;
+      t.mid = (uint16_t)mid;
+      t.sd = (uint8_t)sd;
+      t.kind = 0;
+      S.tab[h] = t;
+      BotTab cl, cr;
+      cl.a = t.a;
+      cl.len = (uint16_t)half;
+      cl.mid = 0;
+      cl.sd = 0;
+      cl.kind = 0;
+      cl.node = t.node + 1;
+      cr.a = (uint16_t)mid;
+      cr.len = (uint16_t)(t.len - half);
+      cr.mid = 0;
+      cr.sd = 0;
+      cr.kind = 0;
+      cr.node = t.node + 1 + nleft;
+      S.tab[2 * h] = cl;
+      S.tab[2 * h + 1] = cr;
+      S.flag = 1;
+    }
+    __syncthreads();
+    depth = lev;
+    if (!S.flag) break;
+    // ---- side flags from the split-dimension list of each segment
+    for (uint32_t i = tid; i < len0; i += BOT_THREADS) {
+      BotTab t = S.tab[S.segh[i]];
+      if (t.kind == 0) S.side[S.lst[cur][t.sd][i]] = (i >= t.mid) ? 1 : 0;
+    }
+    __syncthreads();
+    // ---- stable partition of each list inside every segment
+    for (int d = 0; d < 3; ++d) {
+      uint32_t el[BOT_IPT], bl[BOT_IPT];
+      uint32_t wl = 0;
+#pragma unroll
+      for (int k = 0; k < BOT_IPT; ++k) {
+        uint32_t p = w * (32 * BOT_IPT) + k * 32 + lane;
+        bool valid = p < len0;
+        el[k] = valid ? S.lst[cur][d][p] : 0u;
+        bool isleft = false;
+        if (valid) {
+          BotTab t = S.tab[S.segh[p]];
+          isleft = (t.kind != 0) || (S.side[el[k]] == 0);
+        }
+        bl[k] = __ballot_sync(0xffffffffu, isleft);
+        wl += __popc(bl[k]);
+      }
+      if (lane == 0) S.wtot[w] = wl;
+      __syncthreads();
+      uint32_t pre = 0;
+      for (int k = 0; k < w; ++k) pre += S.wtot[k];
+#pragma unroll
+      for (int k = 0; k < BOT_IPT; ++k) {
+        uint32_t p = w * (32 * BOT_IPT) + k * 32 + lane;
+        if (p < len0) S.scan[p] = (uint16_t)(pre + __popc(bl[k] & lt));
+        pre += __popc(bl[k]);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BOT_IPT; ++k) {
+        uint32_t p = w * (32 * BOT_IPT) + k * 32 + lane;
+        if (p < len0) {
+          BotTab t = S.tab[S.segh[p]];
+          uint32_t dst = p;
+          if (t.kind == 0) {
+            uint32_t before = (uint32_t)S.scan[p] - (uint32_t)S.scan[t.a];  // lefts before me in my segment
+            bool isleft = (bl[k] >> lane) & 1u;
+            dst = isleft ? t.a + before : t.mid + (p - t.a - before);
+          }
+          S.lst[cur ^ 1][d][dst] = (uint16_t)el[k];
+        }
+      }
+      __syncthreads();
+    }
+    // ---- descend: slot -> child segment
+    for (uint32_t i = tid; i < len0; i += BOT_THREADS) {
+      uint32_t h = S.segh[i];
+      BotTab t = S.tab[h];
+      if (t.kind == 0) S.segh[i] = (uint16_t)(2 * h + (i >= t.mid ? 1 : 0));
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+
+  // ---- leaves: ascending id order (canonical), sequential m / sum(m*p) (array_kd_tree.rs:534-539 order of ops)
+  const uint32_t hend = 2u << depth;
+  for (uint32_t h = 1 + tid; h < hend; h += BOT_THREADS) {
+    BotTab t = S.tab[h];
+    if (t.kind != 1) continue;
+    uint32_t g[32];
+    for (uint32_t k = 0; k < t.len; ++k) {
+      uint32_t v = S.gid[S.lst[cur][0][t.a + k]];
+      int j = (int)k - 1;
+      while (j >= 0 && g[j] > v) {
+        g[j + 1] = g[j];
+        --j;
+      }
+      g[j + 1] = v;
+    }
+    double m = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
+    const uint32_t first = a0 + t.a;
+    for (uint32_t k = 0; k < t.len; ++k) {
+      const uint32_t id = g[k];
+      const double mm = mass[id], x = pos.p[0][id], y = pos.p[1][id], z = pos.p[2][id];
+      m = __dadd_rn(m, mm);
+      sx = __dadd_rn(sx, __dmul_rn(mm, x));
+      sy = __dadd_rn(sy, __dmul_rn(mm, y));
+      sz = __dadd_rn(sz, __dmul_rn(mm, z));
+      perm[first + k] = id;
+      rank[id] = first + k;
+      PosM pm;
+      pm.x = x;
+      pm.y = y;
+      pm.z = z;
+      pm.m = mm;
+      posm[first + k] = pm;
+    }
+    ms[t.node] = make_double4(m, sx, sy, sz);
+    WNode* nd = &nodes[t.node];
+    nd->cx = sx;  // not part of the reference's Leaf; kept for debugging only
+    nd->cy = sy;
+    nd->cz = sz;
+    nd->m = m;
+    nd->size2 = 0.0;
+    nd->size = 0.0;
+    nd->split_val = 0.0;
+    nd->a = first;
+    nd->b = t.len;
+  }
+  __syncthreads();
+  // ---- m / cm bottom-up inside this segment: internal = left + right, cm = sum / m (array_kd_tree.rs:548-550)
+  for (int lev = depth - 1; lev >= 0; --lev) {
+    const uint32_t nn = 1u << lev;
+    for (uint32_t h = nn + tid; h < 2 * nn; h += BOT_THREADS) {
+      BotTab t = S.tab[h];
+      if (t.kind != 0) continue;
+      const double4 l = ms[S.tab[2 * h].node], r = ms[S.tab[2 * h + 1].node];
+      double4 s = make_double4(__dadd_rn(l.x, r.x), __dadd_rn(l.y, r.y), __dadd_rn(l.z, r.z), __dadd_rn(l.w, r.w));
+      ms[t.node] = s;
+      WNode* nd = &nodes[t.node];
+      nd->m = s.x;
+      nd->cx = __ddiv_rn(s.y, s.x);
+      nd->cy = __ddiv_rn(s.z, s.x);
+      nd->cz = __ddiv_rn(s.w, s.x);
+    }
+    __syncthreads();
+  }
+}
+
+// m / cm for the global levels (single CTA; at most a few thousand nodes)
+__global__ void __launch_bounds__(1024) build_topup(int l0, const uint32_t* __restrict__ tnode,
+                                                    WNode* __restrict__ nodes, double4* __restrict__ ms) {
+  for (int lev = l0 - 1; lev >= 0; --lev) {
+    const uint32_t nn = 1u << lev, off = nn - 1;
+    for (uint32_t s = threadIdx.x; s < nn; s += blockDim.x) {
+      const uint32_t node = tnode[off + s];
+      WNode* nd = &nodes[node];
+      const double4 l = ms[node + 1], r = ms[nd->a];
+      double4 t = make_double4(__dadd_rn(l.x, r.x), __dadd_rn(l.y, r.y), __dadd_rn(l.z, r.z), __dadd_rn(l.w, r.w));
+      ms[node] = t;
+      nd->m = t.x;
+      nd->cx = __ddiv_rn(t.y, t.x);
+      nd->cy = __ddiv_rn(t.z, t.x);
+      nd->cz = __ddiv_rn(t.w, t.x);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+
+__global__ void fill_unused(WNode* nodes, uint64_t count) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    WNode nd;
+    nd.cx = nd.cy = nd.cz = nd.m = nd.size2 = nd.size = nd.split_val = 0.0;
+    nd.a = 0xFFFFFFFFu;
+    nd.b = WN_UNUSED;
+    nodes[i] = nd;
+  }
+}
+
+void init_unused_nodes(Ctx* c) {
+  if (c->n_nodes == 0) return;
+  KDNB_LAUNCH(c, fill_unused, (unsigned)((c->n_nodes + 255) / 256), 256, 0, c->nodes, c->n_nodes);
+}
+
+static bool g_bottom_attr_set = false;
+
+int build_tree(Ctx* c) {
+  const uint32_t n = (uint32_t)c->n;
+  if (int rc = sort_lists(c)) return rc;
+  if (!g_bottom_attr_set) {
+    KDNB_CUDA_TRY(c, cudaFuncSetAttribute(build_bottom, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(BotSmem)));
+    g_bottom_attr_set = true;
+  }
+  Pos3c pos = {{c->pos[0], c->pos[1], c->pos[2]}};
+  KDNB_LAUNCH(c, build_root, 1, 1, 0, c->tstart, c->tlen, c->tnode, n);
+  int cur = 0;
+  for (int lev = 0; lev < c->l0; ++lev) {
+    const uint32_t nseg = 1u << lev;
+    const uint32_t maxlen = (uint32_t)((c->n + nseg - 1) >> lev);
+    const uint32_t cps = (maxlen + LVL_CHUNK - 1) / LVL_CHUNK;
+    Lists Lin = {{c->list[cur], c->list[cur] + n, c->list[cur] + 2ull * n}};
+    Lists Lout = {{c->list[cur ^ 1], c->list[cur ^ 1] + n, c->list[cur ^ 1] + 2ull * n}};
+    KDNB_LAUNCH(c, level_stats, (nseg + 127) / 128, 128, 0, pos, Lin, lev, c->mp, c->layout, c->tstart, c->tlen,
+                c->tnode, c->tmid, c->tsd, c->nodes);
+    KDNB_LAUNCH(c, level_flags, nseg * cps, LVL_THREADS, 0, Lin, lev, cps, c->tstart, c->tlen, c->tmid, c->tsd,
+                c->side);
+    KDNB_LAUNCH(c, level_count, dim3(nseg * cps, 3), LVL_THREADS, 0, Lin, lev, cps, c->tstart, c->tlen, c->tsd,
+                c->side, c->chunk_cnt);
+    KDNB_LAUNCH(c, level_scan, dim3(nseg, 3), 256, 0, lev, cps, c->tsd, c->chunk_cnt);
+    KDNB_LAUNCH(c, level_scatter, dim3(nseg * cps, 3), LVL_THREADS, 0, Lin, Lout, lev, cps, c->tstart, c->tlen,
+                c->tmid, c->tsd, c->side, c->chunk_cnt);
+    cur ^= 1;
+  }
+  Lists Lb = {{c->list[cur], c->list[cur] + n, c->list[cur] + 2ull * n}};
+  KDNB_LAUNCH(c, build_bottom, 1u << c->l0, BOT_THREADS, sizeof(BotSmem), pos, c->mass, Lb, c->l0, c->mp,
+              c->layout, c->tstart, c->tlen, c->tnode, c->inv, c->nodes, c->ms, c->perm, c->rank, c->posm);
+  if (c->l0 > 0) KDNB_LAUNCH(c, build_topup, 1, 1024, 0, c->l0, c->tnode, c->nodes, c->ms);
+  KDNB_CHECK_LAUNCH(c);
+  c->tree_valid = true;
+  c->map_valid = true;
+  return 0;
+}
+
+// ---- expand device nodes to the C-ABI record (kdnb_node), the mirror of `enum KDTree` (array_kd_tree.rs:18-34)
+__global__ void export_nodes(const WNode* __restrict__ nodes, uint64_t count, kdnb_node* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const WNode nd = nodes[i];
+  kdnb_node o;
+  o.split_dim = 0;
+  o.num_parts = 0;
+  o.leaf_first = KDNB_NO_INDEX;
+  o.split_val = 0.0;
+  o.m = 0.0;
+  o.cm[0] = o.cm[1] = o.cm[2] = 0.0;
+  o.size = 0.0;
+  o.left = 0;
+  o.right = 0;
+  if (nd.b & WN_INTERNAL) {
+    o.kind = KDNB_INTERNAL;
+    o.split_dim = nd.b & 3u;
+    o.split_val = nd.split_val;
+    o.m = nd.m;
+    o.cm[0] = nd.cx;
+    o.cm[1] = nd.cy;
+    o.cm[2] = nd.cz;
+    o.size = nd.size;
+    o.left = i + 1;
+    o.right = nd.a;
+  } else if (nd.b & WN_UNUSED) {
+    o.kind = KDNB_LEAF;
+  } else {
+    o.kind = KDNB_LEAF;
+    o.num_parts = nd.b;
+    o.leaf_first = nd.a;
+  }
+  out[i] = o;
+}
+
+int export_tree(Ctx* c, kdnb_node* dev_out) {
+  KDNB_LAUNCH(c, export_nodes, (unsigned)((c->n_nodes + 255) / 256), 256, 0, c->nodes, c->n_nodes, dev_out);
+  KDNB_CHECK_LAUNCH(c);
+  return 0;
+}
+
+}  // namespace kdnb

@@ -1,0 +1,116 @@
+// ctx.cuh — the context behind the opaque kdnb_ctx handle: device buffers, level plan, stream, counters.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace kdnb {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_IPT = 8;
+constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 2048 keys per CTA
+constexpr int LVL_THREADS = 256;
+constexpr int LVL_CHUNK = 2048;  // list entries per CTA in the global-level partition kernels
+
+struct Ctx {
+  // configuration
+  int device = 0;
+  uint32_t mp = 8;
+  int layout = KDNB_LAYOUT_PADDED;
+  double theta = 0.3, theta2 = 0.09;
+  uint32_t flags = 0;
+  cudaStream_t stream = nullptr;
+
+  // sizes
+  uint64_t n = 0;        // particles (N+1 of the reference)
+  uint64_t cap = 0;      // allocated particle capacity
+  uint64_t n_nodes = 0;  // allocate_node_vec length for (n, layout)
+  uint64_t node_cap = 0;
+  int l0 = 0;            // first level whose segments fit the bottom kernel (<= BOT_CAP)
+  uint32_t ntiles = 0;   // sort tiles
+
+  // particle state, SoA, original order (Particle, array_particle.rs:3-8)
+  double* pos[3] = {nullptr, nullptr, nullptr};
+  double* vel[3] = {nullptr, nullptr, nullptr};
+  double* mass = nullptr;
+  double* radius = nullptr;
+  kdnb_particle* aos = nullptr;  // staging for AoS <-> SoA conversion
+
+  // build scratch
+  uint64_t* keys[2] = {nullptr, nullptr};  // [3][n] radix keys, ping-pong
+  uint32_t* list[2] = {nullptr, nullptr};  // [3][n] per-dimension sorted id lists, ping-pong
+  uint32_t* hist = nullptr;                // [3][256][ntiles]
+  uint32_t* digit_tot = nullptr;           // [3][256]
+  uint8_t* side = nullptr;                 // [n] 0 = goes left, 1 = goes right at the current level
+  uint32_t* inv = nullptr;                 // [n] id -> local slot inside a bottom segment
+  uint32_t* tstart = nullptr;              // level tables, level l at offset 2^l - 1
+  uint32_t* tlen = nullptr;
+  uint32_t* tnode = nullptr;
+  uint32_t* tmid = nullptr;
+  uint8_t* tsd = nullptr;
+  uint32_t* chunk_cnt = nullptr;           // [3][nseg][chunks] left counts per chunk
+  uint64_t table_cap = 0, chunk_cap = 0;
+
+  // tree + tree-ordered views
+  WNode* nodes = nullptr;    // reference node layout (padded or dense indices)
+  double4* ms = nullptr;     // per node {M, sum m*x, sum m*y, sum m*z}
+  uint32_t* perm = nullptr;  // tree slot -> particle id (the reference's `indices` after the build)
+  uint32_t* rank = nullptr;  // particle id -> tree slot
+  PosM* posm = nullptr;      // tree-ordered {x,y,z,m}
+  double* acc_t = nullptr;   // [slots_pad][3] tree-ordered accelerations (the exchanged array)
+  unsigned long long* wcounts = nullptr;  // [n][4] optional walk counters, tree order
+  double* tmp3 = nullptr;    // [n][3] staging for accel up/download
+  bool tree_valid = false, acc_valid = false, map_valid = false;
+  uint64_t planned_n = 0;
+
+  // multi-GPU
+  int rank_id = 0, world = 1;
+  void* nccl_comm = nullptr;
+  uint64_t shard_slots = 0;  // tree slots per rank (multiple of 32)
+
+  // measurement
+  uint64_t launches = 0;
+  std::vector<cudaEvent_t> ev;  // 5 events per profiled step
+  uint64_t ev_steps = 0;
+  cudaEvent_t sw_begin = nullptr, sw_end = nullptr;
+  void* l2_scratch = nullptr;
+
+  mutable std::string err;
+  int fail(int code, const std::string& msg) const {
+    err = msg;
+    return code;
+  }
+};
+
+// sort.cu
+int sort_lists(Ctx* c);
+// build.cu
+int build_tree(Ctx* c);
+int export_tree(Ctx* c, kdnb_node* dev_out);
+void init_unused_nodes(Ctx* c);
+// walk.cu
+int walk(Ctx* c);
+// kick.cu
+int kick_drift(Ctx* c, double dt);
+int aos_to_soa(Ctx* c);
+int soa_to_aos(Ctx* c);
+int gather_acc(Ctx* c, double* dst_orig_order);
+int scatter_acc(Ctx* c, const double* src_orig_order);
+int gather_counts(Ctx* c, unsigned long long* dst_orig_order);
+// peak.cu
+int measure_fp64_peak(Ctx* c, double* tflops);
+
+#define KDNB_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
+  do {                                                                           \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);             \
+    (ctx)->launches++;                                                           \
+  } while (0)
+
+#define KDNB_CHECK_LAUNCH(ctx)                                                   \
+  do {                                                                           \
+    cudaError_t _e = cudaGetLastError();                                         \
+    if (_e != cudaSuccess) return (ctx)->fail(KDNB_E_CUDA, std::string(__FILE__) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+}  // namespace kdnb

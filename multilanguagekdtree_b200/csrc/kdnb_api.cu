@@ -1,0 +1,538 @@
+// kdnb_api.cu — the C ABI of libkdnb.so (include/kdnb.h): context, transfers, the step driver
+// (simple_sim, Parallel/RustVersion/src/array_kd_tree.rs:623-664), NCCL exchange and measurement hooks.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "ctx.cuh"
+
+using namespace kdnb;
+
+struct kdnb_ctx {
+  Ctx c;
+};
+
+static thread_local std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------------ NCCL (dlopen)
+namespace {
+struct NcclId {
+  char internal[128];
+};
+typedef int (*fn_get_unique_id)(NcclId*);
+typedef int (*fn_comm_init_rank)(void**, int, NcclId, int);
+typedef int (*fn_all_gather)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*fn_comm_destroy)(void*);
+typedef const char* (*fn_get_error_string)(int);
+struct NcclApi {
+  void* handle = nullptr;
+  fn_get_unique_id get_unique_id = nullptr;
+  fn_comm_init_rank comm_init_rank = nullptr;
+  fn_all_gather all_gather = nullptr;
+  fn_comm_destroy comm_destroy = nullptr;
+  fn_get_error_string get_error_string = nullptr;
+  bool tried = false;
+} g_nccl;
+
+bool load_nccl(std::string* why) {
+  if (g_nccl.handle) return true;
+  if (!g_nccl.tried) {
+    g_nccl.tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (g_nccl.handle) break;
+    }
+    if (g_nccl.handle) {
+      g_nccl.get_unique_id = (fn_get_unique_id)dlsym(g_nccl.handle, "ncclGetUniqueId");
+      g_nccl.comm_init_rank = (fn_comm_init_rank)dlsym(g_nccl.handle, "ncclCommInitRank");
+      g_nccl.all_gather = (fn_all_gather)dlsym(g_nccl.handle, "ncclAllGather");
+      g_nccl.comm_destroy = (fn_comm_destroy)dlsym(g_nccl.handle, "ncclCommDestroy");
+      g_nccl.get_error_string = (fn_get_error_string)dlsym(g_nccl.handle, "ncclGetErrorString");
+      if (!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.all_gather || !g_nccl.comm_destroy) {
+        dlclose(g_nccl.handle);
+        g_nccl.handle = nullptr;
+      }
+    }
+  }
+  if (!g_nccl.handle && why) *why = "libnccl.so.2 could not be loaded";
+  return g_nccl.handle != nullptr;
+}
+constexpr int NCCL_FLOAT64 = 8;  // ncclDouble
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ helpers
+
+template <typename T>
+static int dev_alloc(Ctx* c, T** p, uint64_t count) {
+  if (*p) {
+    cudaFree(*p);
+    *p = nullptr;
+  }
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e != cudaSuccess) {
+    *p = nullptr;
+    return c->fail(KDNB_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+static void free_all(Ctx* c) {
+  auto fr = [](auto*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  for (int d = 0; d < 3; ++d) {
+    fr(c->pos[d]);
+    fr(c->vel[d]);
+  }
+  fr(c->mass);
+  fr(c->radius);
+  fr(c->aos);
+  fr(c->keys[0]);
+  fr(c->keys[1]);
+  fr(c->list[0]);
+  fr(c->list[1]);
+  fr(c->hist);
+  fr(c->digit_tot);
+  fr(c->side);
+  fr(c->inv);
+  fr(c->tstart);
+  fr(c->tlen);
+  fr(c->tnode);
+  fr(c->tmid);
+  fr(c->tsd);
+  fr(c->chunk_cnt);
+  fr(c->nodes);
+  fr(c->ms);
+  fr(c->perm);
+  fr(c->rank);
+  fr(c->posm);
+  fr(c->acc_t);
+  fr(c->wcounts);
+  fr(c->tmp3);
+}
+
+static uint64_t padded_slots(uint64_t n) { return n + 32ull * 64ull; }
+
+// (re)plan and (re)allocate for `n` particles
+static int plan(Ctx* c, uint64_t n) {
+  if (n == 0) return c->fail(KDNB_E_INVALID, "particle count must be > 0");
+  if (n > 0x7fffff00ull) return c->fail(KDNB_E_INVALID, "particle count exceeds the 32-bit index range of the device path");
+  c->n = n;
+  c->n_nodes = subtree_nodes(n, c->mp, c->layout);
+  c->ntiles = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
+  int l0 = 0;
+  while (((n + (1ull << l0) - 1) >> l0) > (uint64_t)BOT_CAP) ++l0;
+  c->l0 = l0;
+  c->tree_valid = c->acc_valid = c->map_valid = false;
+  const uint64_t table = 2ull << l0;
+  const uint64_t chunks = 3ull * (n / LVL_CHUNK + table + 8);
+  const bool grow = n > c->cap || c->n_nodes > c->node_cap || table > c->table_cap || chunks > c->chunk_cap;
+  if (grow) {
+    free_all(c);
+    c->cap = n;
+    c->node_cap = c->n_nodes;
+    c->table_cap = table;
+    c->chunk_cap = chunks;
+    int rc = 0;
+    for (int d = 0; d < 3 && !rc; ++d) {
+      rc = dev_alloc(c, &c->pos[d], n);
+      if (!rc) rc = dev_alloc(c, &c->vel[d], n);
+    }
+    if (!rc) rc = dev_alloc(c, &c->mass, n);
+    if (!rc) rc = dev_alloc(c, &c->radius, n);
+    if (!rc) rc = dev_alloc(c, &c->aos, std::max<uint64_t>(n, (c->n_nodes * sizeof(kdnb_node) + 63) / 64));
+    if (!rc) rc = dev_alloc(c, &c->keys[0], 3 * n);
+    if (!rc) rc = dev_alloc(c, &c->keys[1], 3 * n);
+    if (!rc) rc = dev_alloc(c, &c->list[0], 3 * n);
+    if (!rc) rc = dev_alloc(c, &c->list[1], 3 * n);
+    if (!rc) rc = dev_alloc(c, &c->hist, 3ull * 256 * c->ntiles);
+    if (!rc) rc = dev_alloc(c, &c->digit_tot, 3 * 256);
+    if (!rc) rc = dev_alloc(c, &c->side, n);
+    if (!rc) rc = dev_alloc(c, &c->inv, n);
+    if (!rc) rc = dev_alloc(c, &c->tstart, table);
+    if (!rc) rc = dev_alloc(c, &c->tlen, table);
+    if (!rc) rc = dev_alloc(c, &c->tnode, table);
+    if (!rc) rc = dev_alloc(c, &c->tmid, table);
+    if (!rc) rc = dev_alloc(c, &c->tsd, table);
+    if (!rc) rc = dev_alloc(c, &c->chunk_cnt, chunks);
+    if (!rc) rc = dev_alloc(c, &c->nodes, c->n_nodes);
+    if (!rc) rc = dev_alloc(c, &c->ms, c->n_nodes);
+    if (!rc) rc = dev_alloc(c, &c->perm, n);
+    if (!rc) rc = dev_alloc(c, &c->rank, n);
+    if (!rc) rc = dev_alloc(c, &c->posm, n);
+    if (!rc) rc = dev_alloc(c, &c->acc_t, 3 * padded_slots(n));
+    if (!rc && (c->flags & KDNB_FLAG_WALK_COUNTS)) rc = dev_alloc(c, &c->wcounts, 4 * n);
+    if (!rc) rc = dev_alloc(c, &c->tmp3, 4 * n);
+    if (rc) {
+      free_all(c);
+      c->cap = c->node_cap = c->table_cap = c->chunk_cap = 0;
+      c->n = 0;
+      return rc;
+    }
+  }
+  if (grow || c->planned_n != n) {
+    KDNB_CUDA_TRY(c, cudaMemsetAsync(c->acc_t, 0, 3 * padded_slots(n) * sizeof(double), c->stream));
+    init_unused_nodes(c);  // slots the build never writes keep the reference's default Leaf{0, NEGS}
+    c->planned_n = n;
+  }
+  if (c->world > 1) c->shard_slots = (((n + c->world - 1) / c->world) + 31) / 32 * 32;
+  return 0;
+}
+
+static int exchange(Ctx* c) {
+  if (c->world <= 1) return 0;
+  const size_t count = (size_t)c->shard_slots * 3;
+  int r = g_nccl.all_gather(c->acc_t + (size_t)c->rank_id * count, c->acc_t, count, NCCL_FLOAT64, c->nccl_comm, c->stream);
+  if (r != 0)
+    return c->fail(KDNB_E_NCCL, std::string("ncclAllGather: ") + (g_nccl.get_error_string ? g_nccl.get_error_string(r) : "error"));
+  return 0;
+}
+
+static int one_step(Ctx* c, double dt) {
+  const bool prof = (c->flags & KDNB_FLAG_PROFILE) && c->ev_steps < 4096;
+  cudaEvent_t* e = nullptr;
+  if (prof) {
+    if (c->ev.size() < (c->ev_steps + 1) * 5) {
+      for (int k = 0; k < 5; ++k) {
+        cudaEvent_t x;
+        KDNB_CUDA_TRY(c, cudaEventCreate(&x));
+        c->ev.push_back(x);
+      }
+    }
+    e = &c->ev[c->ev_steps * 5];
+    cudaEventRecord(e[0], c->stream);
+  }
+  if (int rc = build_tree(c)) return rc;  // indices reset + build_tree_par4 (:641-643)
+  if (prof) cudaEventRecord(e[1], c->stream);
+  if (int rc = walk(c)) return rc;        // calc_accel for every particle (:647)
+  if (prof) cudaEventRecord(e[2], c->stream);
+  if (int rc = exchange(c)) return rc;
+  if (prof) cudaEventRecord(e[3], c->stream);
+  if (int rc = kick_drift(c, dt)) return rc;  // (:649-662)
+  if (prof) {
+    cudaEventRecord(e[4], c->stream);
+    c->ev_steps++;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+int kdnb_version(void) { return KDNB_VERSION; }
+
+const char* kdnb_last_error(const kdnb_ctx* ctx) { return ctx ? ctx->c.err.c_str() : g_create_error.c_str(); }
+
+kdnb_ctx* kdnb_create(const kdnb_config* cfg) {
+  kdnb_config k;
+  memset(&k, 0, sizeof k);
+  if (cfg) memcpy(&k, cfg, std::min<size_t>(sizeof k, cfg->struct_size ? cfg->struct_size : sizeof k));
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                     " (libkdnb has no CPU fallback)";
+    return nullptr;
+  }
+  if (k.device < 0 || k.device >= ndev) {
+    g_create_error = "device ordinal out of range";
+    return nullptr;
+  }
+  const uint32_t mp = k.max_parts ? k.max_parts : 8;
+  if (mp < 4 || mp > 32) {
+    g_create_error = "max_parts must be in 4..32";
+    return nullptr;
+  }
+  if (k.layout != KDNB_LAYOUT_PADDED && k.layout != KDNB_LAYOUT_DENSE) {
+    g_create_error = "unknown layout";
+    return nullptr;
+  }
+  kdnb_ctx* h = new (std::nothrow) kdnb_ctx();
+  if (!h) {
+    g_create_error = "out of host memory";
+    return nullptr;
+  }
+  Ctx* c = &h->c;
+  c->device = k.device;
+  c->mp = mp;
+  c->layout = k.layout;
+  c->theta = k.theta != 0.0 ? k.theta : 0.3;
+  c->theta2 = c->theta * c->theta;  // THETA * THETA (array_kd_tree.rs:606)
+  c->flags = k.flags;
+  if ((e = cudaSetDevice(c->device)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&c->sw_begin)) != cudaSuccess || (e = cudaEventCreate(&c->sw_end)) != cudaSuccess) {
+    g_create_error = std::string("CUDA init: ") + cudaGetErrorString(e);
+    delete h;
+    return nullptr;
+  }
+  return h;
+}
+
+void kdnb_destroy(kdnb_ctx* ctx) {
+  if (!ctx) return;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->nccl_comm && g_nccl.comm_destroy) g_nccl.comm_destroy(c->nccl_comm);
+  free_all(c);
+  if (c->l2_scratch) cudaFree(c->l2_scratch);
+  for (cudaEvent_t x : c->ev) cudaEventDestroy(x);
+  if (c->sw_begin) cudaEventDestroy(c->sw_begin);
+  if (c->sw_end) cudaEventDestroy(c->sw_end);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete ctx;
+}
+
+#define CTX_OR_FAIL(ctx)                 \
+  if (!(ctx)) return KDNB_E_INVALID;     \
+  Ctx* c = &(ctx)->c;                    \
+  KDNB_CUDA_TRY(c, cudaSetDevice(c->device))
+
+int kdnb_upload_particles(kdnb_ctx* ctx, const kdnb_particle* aos, uint64_t count) {
+  CTX_OR_FAIL(ctx);
+  if (!aos) return c->fail(KDNB_E_INVALID, "null particle array");
+  if (int rc = plan(c, count)) return rc;
+  KDNB_CUDA_TRY(c, cudaMemcpyAsync(c->aos, aos, count * sizeof(kdnb_particle), cudaMemcpyHostToDevice, c->stream));
+  return aos_to_soa(c);
+}
+
+int kdnb_download_particles(kdnb_ctx* ctx, kdnb_particle* out, uint64_t capacity) {
+  CTX_OR_FAIL(ctx);
+  if (!out) return c->fail(KDNB_E_INVALID, "null output array");
+  if (c->n == 0) return c->fail(KDNB_E_INVALID, "no particles uploaded");
+  if (capacity < c->n) return c->fail(KDNB_E_CAPACITY, "output array smaller than the particle count");
+  if (int rc = soa_to_aos(c)) return rc;
+  KDNB_CUDA_TRY(c, cudaMemcpyAsync(out, c->aos, c->n * sizeof(kdnb_particle), cudaMemcpyDeviceToHost, c->stream));
+  KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+uint64_t kdnb_particle_count(const kdnb_ctx* ctx) { return ctx ? ctx->c.n : 0; }
+
+int kdnb_build_tree(kdnb_ctx* ctx) {
+  CTX_OR_FAIL(ctx);
+  if (c->n == 0) return c->fail(KDNB_E_INVALID, "no particles uploaded");
+  return build_tree(c);
+}
+
+int kdnb_calc_accel(kdnb_ctx* ctx) {
+  CTX_OR_FAIL(ctx);
+  if (!c->tree_valid) return c->fail(KDNB_E_INVALID, "kdnb_calc_accel needs kdnb_build_tree on the current positions first");
+  if (int rc = walk(c)) return rc;
+  return exchange(c);
+}
+
+int kdnb_kick_drift(kdnb_ctx* ctx, double dt) {
+  CTX_OR_FAIL(ctx);
+  if (c->n == 0) return c->fail(KDNB_E_INVALID, "no particles uploaded");
+  if (!c->map_valid) return c->fail(KDNB_E_INVALID, "kdnb_kick_drift needs the particle->slot map of a previous kdnb_build_tree");
+  return kick_drift(c, dt);
+}
+
+int kdnb_simple_sim(kdnb_ctx* ctx, double dt, int64_t steps) {
+  CTX_OR_FAIL(ctx);
+  if (c->n == 0) return c->fail(KDNB_E_INVALID, "no particles uploaded");
+  for (int64_t s = 0; s < steps; ++s)
+    if (int rc = one_step(c, dt)) return rc;
+  return 0;
+}
+
+int kdnb_simple_sim_bodies(kdnb_ctx* ctx, kdnb_particle* bodies, uint64_t count, double dt, int64_t steps) {
+  if (int rc = kdnb_upload_particles(ctx, bodies, count)) return rc;
+  if (int rc = kdnb_simple_sim(ctx, dt, steps)) return rc;
+  return kdnb_download_particles(ctx, bodies, count);
+}
+
+int kdnb_simple_sim_host(const kdnb_config* cfg, kdnb_particle* bodies, uint64_t count, double dt, int64_t steps) {
+  kdnb_ctx* h = kdnb_create(cfg);
+  if (!h) return KDNB_E_CUDA;
+  int rc = kdnb_simple_sim_bodies(h, bodies, count, dt, steps);
+  if (rc) g_create_error = h->c.err;
+  kdnb_destroy(h);
+  return rc;
+}
+
+int kdnb_synchronize(kdnb_ctx* ctx) {
+  CTX_OR_FAIL(ctx);
+  KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int kdnb_download_accel(kdnb_ctx* ctx, double* acc) {
+  CTX_OR_FAIL(ctx);
+  if (!acc) return c->fail(KDNB_E_INVALID, "null output array");
+  if (c->n == 0) return c->fail(KDNB_E_INVALID, "no particles uploaded");
+  if (!c->tree_valid) {
+    // before any build (or after a kick) the reference's acc vector is all zeros (:624-627, :659-661)
+    memset(acc, 0, 3 * c->n * sizeof(double));
+    return 0;
+  }
+  if (int rc = gather_acc(c, c->tmp3)) return rc;
+  KDNB_CUDA_TRY(c, cudaMemcpyAsync(acc, c->tmp3, 3 * c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int kdnb_upload_accel(kdnb_ctx* ctx, const double* acc) {
+  CTX_OR_FAIL(ctx);
+  if (!acc) return c->fail(KDNB_E_INVALID, "null input array");
+  if (!c->tree_valid) return c->fail(KDNB_E_INVALID, "kdnb_upload_accel needs a built tree (particle->slot map)");
+  KDNB_CUDA_TRY(c, cudaMemcpyAsync(c->tmp3, acc, 3 * c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (int rc = scatter_acc(c, c->tmp3)) return rc;
+  c->acc_valid = true;
+  return 0;
+}
+
+int kdnb_download_tree(kdnb_ctx* ctx, kdnb_node* nodes, uint64_t cap, uint64_t* n_nodes, uint64_t* indices) {
+  CTX_OR_FAIL(ctx);
+  if (!c->tree_valid) return c->fail(KDNB_E_INVALID, "no tree built for the current positions");
+  if (n_nodes) *n_nodes = c->n_nodes;
+  if (nodes) {
+    if (cap < c->n_nodes) return c->fail(KDNB_E_CAPACITY, "node array smaller than kdnb_node_count()");
+    kdnb_node* dev = reinterpret_cast<kdnb_node*>(c->aos);  // staging buffer is sized for this in plan()
+    if (int rc = export_tree(c, dev)) return rc;
+    KDNB_CUDA_TRY(c, cudaMemcpyAsync(nodes, dev, c->n_nodes * sizeof(kdnb_node), cudaMemcpyDeviceToHost, c->stream));
+  }
+  KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (indices) {
+    std::vector<uint32_t> tmp(c->n);
+    KDNB_CUDA_TRY(c, cudaMemcpy(tmp.data(), c->perm, c->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < c->n; ++i) indices[i] = tmp[i];
+  }
+  return 0;
+}
+
+int kdnb_download_walk_counts(kdnb_ctx* ctx, uint64_t* counts) {
+  CTX_OR_FAIL(ctx);
+  if (!(c->flags & KDNB_FLAG_WALK_COUNTS)) return c->fail(KDNB_E_INVALID, "context was created without KDNB_FLAG_WALK_COUNTS");
+  if (!c->acc_valid || !c->tree_valid) return c->fail(KDNB_E_INVALID, "no walk results for the current tree");
+  unsigned long long* dev = reinterpret_cast<unsigned long long*>(c->tmp3);
+  if (int rc = gather_counts(c, dev)) return rc;
+  KDNB_CUDA_TRY(c, cudaMemcpyAsync(counts, dev, 4 * c->n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+  KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+uint64_t kdnb_nodes_needed(uint64_t num_parts, uint32_t max_parts) {
+  if (max_parts < 2) return 0;
+  return nodes_needed_padded(num_parts, max_parts);
+}
+
+uint64_t kdnb_node_count(const kdnb_ctx* ctx) { return ctx ? ctx->c.n_nodes : 0; }
+
+int kdnb_comm_unique_id(void* id_out) {
+  std::string why;
+  if (!id_out || !load_nccl(&why)) {
+    g_create_error = why;
+    return KDNB_E_NCCL;
+  }
+  NcclId id;
+  int r = g_nccl.get_unique_id(&id);
+  if (r != 0) return KDNB_E_NCCL;
+  memcpy(id_out, &id, sizeof id);
+  return 0;
+}
+
+int kdnb_comm_init(kdnb_ctx* ctx, const void* id_bytes, int rank, int world_size) {
+  CTX_OR_FAIL(ctx);
+  if (world_size < 1 || rank < 0 || rank >= world_size || world_size > 64) return c->fail(KDNB_E_INVALID, "bad rank / world size");
+  if (world_size == 1) {
+    c->rank_id = 0;
+    c->world = 1;
+    return 0;
+  }
+  std::string why;
+  if (!id_bytes || !load_nccl(&why)) return c->fail(KDNB_E_NCCL, why.empty() ? "null NCCL id" : why);
+  NcclId id;
+  memcpy(&id, id_bytes, sizeof id);
+  void* comm = nullptr;
+  int r = g_nccl.comm_init_rank(&comm, world_size, id, rank);
+  if (r != 0)
+    return c->fail(KDNB_E_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.get_error_string ? g_nccl.get_error_string(r) : "error"));
+  c->nccl_comm = comm;
+  c->rank_id = rank;
+  c->world = world_size;
+  if (c->n) c->shard_slots = (((c->n + c->world - 1) / c->world) + 31) / 32 * 32;
+  return 0;
+}
+
+int kdnb_stage_ms(kdnb_ctx* ctx, double ms_out[KDNB_STAGE_COUNT], uint64_t* steps_out) {
+  CTX_OR_FAIL(ctx);
+  if (!(c->flags & KDNB_FLAG_PROFILE)) return c->fail(KDNB_E_INVALID, "context was created without KDNB_FLAG_PROFILE");
+  KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < KDNB_STAGE_COUNT; ++k) ms_out[k] = 0.0;
+  for (uint64_t s = 0; s < c->ev_steps; ++s) {
+    cudaEvent_t* e = &c->ev[s * 5];
+    float t;
+    cudaEventElapsedTime(&t, e[0], e[1]);
+    ms_out[KDNB_STAGE_BUILD] += t;
+    cudaEventElapsedTime(&t, e[1], e[2]);
+    ms_out[KDNB_STAGE_WALK] += t;
+    cudaEventElapsedTime(&t, e[2], e[3]);
+    ms_out[KDNB_STAGE_EXCHANGE] += t;
+    cudaEventElapsedTime(&t, e[3], e[4]);
+    ms_out[KDNB_STAGE_KICK] += t;
+  }
+  if (steps_out) *steps_out = c->ev_steps;
+  return 0;
+}
+
+int kdnb_stage_reset(kdnb_ctx* ctx) {
+  CTX_OR_FAIL(ctx);
+  KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->ev_steps = 0;
+  return 0;
+}
+
+uint64_t kdnb_launch_count(const kdnb_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+int kdnb_measure_fp64_peak(kdnb_ctx* ctx, double* tflops_out) {
+  CTX_OR_FAIL(ctx);
+  if (!tflops_out) return c->fail(KDNB_E_INVALID, "null output");
+  return measure_fp64_peak(c, tflops_out);
+}
+
+int kdnb_flush_l2(kdnb_ctx* ctx) {
+  CTX_OR_FAIL(ctx);
+  const size_t bytes = 256ull << 20;
+  if (!c->l2_scratch) {
+    cudaError_t e = cudaMalloc(&c->l2_scratch, bytes);
+    if (e != cudaSuccess) return c->fail(KDNB_E_NOMEM, "cudaMalloc(l2 scratch)");
+  }
+  KDNB_CUDA_TRY(c, cudaMemsetAsync(c->l2_scratch, (int)(c->launches & 0xff), bytes, c->stream));
+  return 0;
+}
+
+int kdnb_device_ms(kdnb_ctx* ctx, int begin_or_end, double* ms_out) {
+  CTX_OR_FAIL(ctx);
+  if (begin_or_end == 0) {
+    KDNB_CUDA_TRY(c, cudaEventRecord(c->sw_begin, c->stream));
+    return 0;
+  }
+  KDNB_CUDA_TRY(c, cudaEventRecord(c->sw_end, c->stream));
+  KDNB_CUDA_TRY(c, cudaEventSynchronize(c->sw_end));
+  float t = 0.f;
+  KDNB_CUDA_TRY(c, cudaEventElapsedTime(&t, c->sw_begin, c->sw_end));
+  if (ms_out) *ms_out = t;
+  return 0;
+}
+
+void* kdnb_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+
+void kdnb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,184 @@
+// sort.cu — per-dimension sorted id lists: a hand-written stable LSD radix sort (8 passes x 8 bits) of the
+// order-preserving 64-bit keys of the x, y and z coordinates, all three dimensions batched in one launch
+// (blockIdx.y = dimension).  Starting from ids 0..n-1 and being stable, equal coordinates stay in ascending
+// particle-id order: the canonical tie-break of the build (SURVEY.md §7 hard part 1).
+//
+// This replaces, together with build.cu, the random-pivot quick-select of the reference
+// (Parallel/RustVersion/src/quickstat.rs:9-34 called from array_kd_tree.rs:561-562): with the three lists
+// sorted once per step, every node's median is the middle entry of its list segment and the bounding box
+// is its two ends.
+#include "ctx.cuh"
+
+namespace kdnb {
+
+struct Pos3 {
+  const double* p[3];
+};
+
+// ---- pass kernel 1: per-tile digit histogram
+template <bool FIRST>
+__global__ void __launch_bounds__(SORT_THREADS) sort_upsweep(Pos3 pos, const uint64_t* __restrict__ keys_in,
+                                                             uint32_t n, int shift, uint32_t ntiles,
+                                                             uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[256];
+  const int d = blockIdx.y;
+  const uint32_t tile = blockIdx.x;
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t base = (uint64_t)tile * SORT_TILE;
+#pragma unroll
+  for (int k = 0; k < SORT_IPT; ++k) {
+    uint64_t i = base + (uint64_t)k * SORT_THREADS + threadIdx.x;
+    if (i < n) {
+      uint64_t key = FIRST ? f64_key(pos.p[d][i]) : keys_in[(uint64_t)d * n + i];
+      atomicAdd(&h[(key >> shift) & 255u], 1u);
+    }
+  }
+  __syncthreads();
+  hist[((uint64_t)d * 256 + threadIdx.x) * ntiles + tile] = h[threadIdx.x];
+}
+
+// ---- pass kernel 2: exclusive scan of every (dimension, digit) row over tiles; row totals to tot[]
+__global__ void __launch_bounds__(256) sort_scan_rows(uint32_t* __restrict__ hist, uint32_t ntiles,
+                                                      uint32_t* __restrict__ tot) {
+  __shared__ uint32_t wsum[8];
+  uint32_t* row = hist + ((uint64_t)blockIdx.y * 256 + blockIdx.x) * ntiles;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < ntiles; base += 256) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < ntiles ? row[i] : 0u;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    uint32_t wp = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      uint32_t t = wsum[k];
+      if (k < w) wp += t;
+      total += t;
+    }
+    if (i < ntiles) row[i] = carry + wp + x - v;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tot[blockIdx.y * 256 + blockIdx.x] = carry;
+}
+
+// ---- pass kernel 3: stable rank inside the tile (warp match), scatter
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const uint64_t* __restrict__ keys_in,
+                                                               const uint32_t* __restrict__ vals_in,
+                                                               uint64_t* __restrict__ keys_out,
+                                                               uint32_t* __restrict__ vals_out, uint32_t n,
+                                                               int shift, uint32_t ntiles,
+                                                               const uint32_t* __restrict__ hist,
+                                                               const uint32_t* __restrict__ tot) {
+  __shared__ uint32_t wcnt[SORT_THREADS / 32][256];
+  __shared__ uint32_t base[256];
+  __shared__ uint32_t wsum[8];
+  const int d = blockIdx.y;
+  const uint32_t tile = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+
+#pragma unroll
+  for (int k = 0; k < SORT_THREADS / 32; ++k) wcnt[k][threadIdx.x] = 0;
+  {  // global base of every digit: exclusive scan of the 256 digit totals + this tile's row prefix
+    uint32_t v = tot[d * 256 + threadIdx.x];
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    uint32_t wp = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < w) wp += wsum[k];
+    base[threadIdx.x] = wp + x - v + hist[((uint64_t)d * 256 + threadIdx.x) * ntiles + tile];
+  }
+  __syncthreads();
+
+  uint64_t key[SORT_IPT];
+  uint32_t val[SORT_IPT], rk[SORT_IPT];
+  const uint64_t start = (uint64_t)tile * SORT_TILE + (uint64_t)w * (32 * SORT_IPT);
+#pragma unroll
+  for (int r = 0; r < SORT_IPT; ++r) {
+    uint64_t i = start + r * 32 + lane;
+    bool valid = i < n;
+    key[r] = valid ? (FIRST ? f64_key(pos.p[d][i]) : keys_in[(uint64_t)d * n + i]) : ~0ull;
+    val[r] = valid ? (FIRST ? (uint32_t)i : vals_in[(uint64_t)d * n + i]) : 0u;
+    uint32_t dg = valid ? (uint32_t)((key[r] >> shift) & 255u) : 256u;
+    uint32_t peers = __match_any_sync(0xffffffffu, dg);
+    int leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (valid && lane == leader) {
+      old = wcnt[w][dg];
+      wcnt[w][dg] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rk[r] = old + __popc(peers & lt);
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // exclusive scan over warps, per digit
+    uint32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < SORT_THREADS / 32; ++k) {
+      uint32_t t = wcnt[k][threadIdx.x];
+      wcnt[k][threadIdx.x] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < SORT_IPT; ++r) {
+    uint64_t i = start + r * 32 + lane;
+    if (i < n) {
+      uint32_t dg = (uint32_t)((key[r] >> shift) & 255u);
+      uint64_t dst = (uint64_t)d * n + base[dg] + wcnt[w][dg] + rk[r];
+      if (!LAST) keys_out[dst] = key[r];
+      vals_out[dst] = val[r];
+    }
+  }
+}
+
+// Sorted lists end in c->list[0] (8 passes: positions -> buf1 -> buf0 -> ... -> buf0).
+int sort_lists(Ctx* c) {
+  const uint32_t n = (uint32_t)c->n;
+  const uint32_t nt = c->ntiles;
+  Pos3 pos = {{c->pos[0], c->pos[1], c->pos[2]}};
+  dim3 gt(nt, 3), gs(256, 3);
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = 8 * pass;
+    const int src = (pass & 1) ? 1 : 0, dst = src ^ 1;  // pass 0 reads positions, writes buf1
+    if (pass == 0) {
+      KDNB_LAUNCH(c, sort_upsweep<true>, gt, SORT_THREADS, 0, pos, nullptr, n, shift, nt, c->hist);
+    } else {
+      KDNB_LAUNCH(c, sort_upsweep<false>, gt, SORT_THREADS, 0, pos, c->keys[src], n, shift, nt, c->hist);
+    }
+    KDNB_LAUNCH(c, sort_scan_rows, gs, 256, 0, c->hist, nt, c->digit_tot);
+    if (pass == 0) {
+      KDNB_LAUNCH(c, (sort_downsweep<true, false>), gt, SORT_THREADS, 0, pos, nullptr, nullptr, c->keys[1],
+                  c->list[1], n, shift, nt, c->hist, c->digit_tot);
+    } else if (pass == 7) {
+      KDNB_LAUNCH(c, (sort_downsweep<false, true>), gt, SORT_THREADS, 0, pos, c->keys[src], c->list[src],
+                  c->keys[dst], c->list[dst], n, shift, nt, c->hist, c->digit_tot);
+    } else {
+      KDNB_LAUNCH(c, (sort_downsweep<false, false>), gt, SORT_THREADS, 0, pos, c->keys[src], c->list[src],
+                  c->keys[dst], c->list[dst], n, shift, nt, c->hist, c->digit_tot);
+    }
+  }
+  KDNB_CHECK_LAUNCH(c);
+  return 0;
+}
+
+}  // namespace kdnb

@@ -1,0 +1,355 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libkdnb.so), against the CPU oracle on the same inputs.
+
+Contract:
+  bit-exact : node index layout, kind, num_parts, leaf membership, indices, split_dim, split_val, size, left, right,
+              and m / cm against the oracle's canonical summation order; kick/drift given identical accelerations;
+              per-particle counts of node tests / accepts / leaf visits / pair interactions (i.e. every acceptance decision)
+  tolerance : accelerations <= 1e-12 relative (vector norm) against the oracle's pairwise walk; positions after K steps
+              <= 1e-12 relative; m / cm against the FAITHFUL (reference summation order) oracle <= 1e-11.
+"""
+import numpy as np
+import pytest
+
+import multilanguagekdtree_b200 as kd
+from oracle.okd import LAYOUT_DENSE as O_DENSE
+from oracle.okd import LAYOUT_PADDED as O_PADDED
+from oracle.okd import ORDER_CANONICAL, ORDER_FAITHFUL, PARTICLE
+
+pytestmark = pytest.mark.gpu
+
+ACC_RTOL = 1e-12
+POS_RTOL = 1e-12
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def to_oracle_nodes(orc, nodes, indices, max_parts):
+    """kdnb_node records -> the oracle's okd_node records (for its walk / invariant checker)."""
+    out = orc.allocate_node_vec(len(nodes))
+    internal = nodes["kind"] == kd.INTERNAL
+    out["is_internal"] = internal
+    lp = kd.leaf_parts(nodes, indices, orc.leaf_cap)
+    leaf = ~internal
+    out["num_parts"][leaf] = nodes["num_parts"][leaf]
+    out["leaf_parts"][leaf] = lp[leaf]
+    for f in ("split_dim", "split_val", "m", "cm", "size", "left", "right"):
+        out[f][internal] = nodes[f][internal]
+    return out
+
+
+def assert_tree_bit_exact(orc, gnodes, gidx, onodes, oidx, max_parts, sums_exact=True):
+    assert len(gnodes) >= len(onodes) or len(onodes) >= len(gnodes)
+    n = min(len(gnodes), len(onodes))
+    g, o = gnodes[:n], onodes[:n]
+    internal = o["is_internal"].astype(bool)
+    assert np.array_equal(g["kind"] == kd.INTERNAL, internal)
+    for f in ("split_dim", "left", "right"):
+        assert np.array_equal(g[f][internal].astype(np.uint64), o[f][internal]), f
+    for f in ("split_val", "size"):
+        assert np.array_equal(g[f][internal], o[f][internal]), f          # value-exact (-0.0 == +0.0)
+    leaf = ~internal
+    assert np.array_equal(g["num_parts"][leaf], o["num_parts"][leaf])
+    glp = kd.leaf_parts(g, gidx, orc.leaf_cap)
+    used = leaf & (o["num_parts"] > 0)
+    assert np.array_equal(glp[used], o["leaf_parts"][used])                # canonical order: ascending ids, 0 padding
+    unused = leaf & (o["num_parts"] == 0)
+    assert np.all(glp[unused] == np.uint64(kd.NO_INDEX)) and np.all(o["leaf_parts"][unused] == np.uint64(kd.NO_INDEX))
+    assert np.array_equal(gidx, oidx)
+    if sums_exact:
+        assert np.array_equal(bits(g["m"][internal]), bits(o["m"][internal]))
+        assert np.array_equal(bits(g["cm"][internal]), bits(o["cm"][internal]))
+
+
+def cube(n, seed, quant=None, equal_mass=True):
+    rng = np.random.default_rng(seed)
+    parts = np.zeros(n, PARTICLE)
+    p = rng.random((n, 3)) * 2.0 - 1.0
+    if quant:
+        p = np.round(p * quant) / quant       # many exactly equal coordinates: exercises the tie-break
+    parts["p"] = p
+    parts["v"] = rng.normal(size=(n, 3)) * 0.1
+    parts["m"] = 1.0 / n if equal_mass else rng.random(n) / n
+    parts["r"] = 1e-3
+    return parts
+
+
+@pytest.mark.parametrize("n", [1, 2, 8, 9, 11, 16, 17, 100, 1000, 2047, 2048, 2049, 5000, 4096 * 3 + 5, 100000])
+def test_build_padded_ring_bit_exact(orc, n):
+    parts = orc.circular_orbits(n, seed=1000 + n)
+    with kd.KDTreeSim() as sim:
+        sim.upload(parts)
+        sim.build_tree()
+        gnodes, gidx = sim.tree()
+    onodes, oidx, _ = orc.build_tree_canonical(parts, layout=O_PADDED, threads=8)
+    assert len(gnodes) == len(onodes) == orc.nodes_needed_for_particles(n + 1, 8)
+    assert_tree_bit_exact(orc, gnodes, gidx, onodes, oidx, 8)
+    assert orc.check_tree_struct(to_oracle_nodes(orc, gnodes, gidx, 8), parts) == 0   # array_kd_tree.rs:834-877
+
+
+@pytest.mark.parametrize("n", [3, 12, 500, 5001, 70001])
+def test_build_dense_bit_exact(orc, n):
+    parts = orc.circular_orbits(n - 1, seed=n)
+    with kd.KDTreeSim(layout=kd.LAYOUT_DENSE) as sim:
+        sim.upload(parts)
+        sim.build_tree()
+        gnodes, gidx = sim.tree()
+    onodes, oidx, last = orc.build_tree_canonical(parts, layout=O_DENSE)
+    assert len(gnodes) == last + 1
+    assert_tree_bit_exact(orc, gnodes, gidx, onodes[: last + 1], oidx, 8)
+
+
+@pytest.mark.parametrize("mp,layout", [(7, kd.LAYOUT_DENSE), (4, kd.LAYOUT_PADDED), (5, kd.LAYOUT_DENSE)])
+def test_build_other_max_parts(orc, mp, layout):
+    parts = orc.circular_orbits(20000, seed=mp)
+    with kd.KDTreeSim(max_parts=mp, layout=layout) as sim:
+        sim.upload(parts)
+        sim.build_tree()
+        gnodes, gidx = sim.tree()
+    onodes, oidx, last = orc.build_tree_canonical(parts, max_parts=mp, layout=O_PADDED if layout == kd.LAYOUT_PADDED else O_DENSE)
+    assert_tree_bit_exact(orc, gnodes, gidx, onodes[: len(gnodes)], oidx, mp)
+
+
+@pytest.mark.parametrize("mp", [16, 32])
+def test_build_large_leaves(orc32, mp):
+    parts = orc32.circular_orbits(30000, seed=mp)
+    with kd.KDTreeSim(max_parts=mp) as sim:
+        sim.upload(parts)
+        sim.build_tree()
+        gnodes, gidx = sim.tree()
+    onodes, oidx, _ = orc32.build_tree_canonical(parts, max_parts=mp)
+    assert_tree_bit_exact(orc32, gnodes, gidx, onodes, oidx, mp)
+
+
+@pytest.mark.parametrize("n,quant", [(5000, None), (40000, None), (30000, 64), (3000, 4)])
+def test_build_3d_and_ties_bit_exact(orc, n, quant):
+    parts = cube(n, seed=n, quant=quant, equal_mass=False)
+    with kd.KDTreeSim() as sim:
+        sim.upload(parts)
+        sim.build_tree()
+        gnodes, gidx = sim.tree()
+    onodes, oidx, _ = orc.build_tree_canonical(parts, threads=4)
+    assert_tree_bit_exact(orc, gnodes, gidx, onodes, oidx, 8)
+    assert set(np.unique(gnodes["split_dim"][gnodes["kind"] == kd.INTERNAL])) == {0, 1, 2}
+
+
+def test_build_vs_faithful_reference_order(orc):
+    """Against the reference's own summation order (random pivots): everything order-independent is bit-exact,
+    m / cm agree to the reference's run-to-run noise."""
+    parts = orc.circular_orbits(50000, seed=77)
+    with kd.KDTreeSim() as sim:
+        sim.upload(parts)
+        sim.build_tree()
+        g, gidx = sim.tree()
+    o, oidx = orc.build_tree_par4(parts, seed=5, threads=4)
+    internal = o["is_internal"].astype(bool)
+    assert np.array_equal(g["kind"] == kd.INTERNAL, internal)
+    for f in ("split_dim", "left", "right"):
+        assert np.array_equal(g[f][internal].astype(np.uint64), o[f][internal])
+    for f in ("split_val", "size"):
+        assert np.array_equal(g[f][internal], o[f][internal])
+    glp = kd.leaf_parts(g, gidx)
+    leaf = ~internal & (o["num_parts"] > 0)
+    assert np.array_equal(g["num_parts"][leaf], o["num_parts"][leaf])
+    assert np.array_equal(np.sort(glp[leaf], axis=1), np.sort(o["leaf_parts"][leaf], axis=1))   # leaf membership as sets
+    assert np.allclose(g["m"][internal], o["m"][internal], rtol=1e-11, atol=0)
+    assert np.allclose(g["cm"][internal], o["cm"][internal], rtol=0, atol=1e-11)
+
+
+def _walk_case(orc, parts, flags=0, theta=0.3, mp=8):
+    with kd.KDTreeSim(flags=flags | kd.FLAG_WALK_COUNTS, theta=theta, max_parts=mp) as sim:
+        sim.upload(parts)
+        sim.build_tree()
+        sim.calc_accel()
+        acc = sim.accel()
+        cnt = sim.walk_counts()
+        gnodes, gidx = sim.tree()
+    onodes = to_oracle_nodes(orc, gnodes, gidx, mp)
+    oacc, ocnt = orc.calc_accel_all(parts, onodes, theta=theta, counts=True)
+    return acc, cnt, oacc, ocnt
+
+
+def rel_err(a, b):
+    return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-300)
+
+
+@pytest.mark.parametrize("n", [1, 11, 1000, 5000, 100000])
+def test_walk_ring_acc_and_decisions(orc, n):
+    parts = orc.circular_orbits(n, seed=n + 5)
+    acc, cnt, oacc, ocnt = _walk_case(orc, parts)
+    for k, f in enumerate(("node_visits", "accepts", "leaf_visits", "pp")):
+        assert np.array_equal(cnt[:, k], ocnt[f]), f       # every open/accept decision identical to the reference's
+    assert rel_err(acc, oacc).max() <= ACC_RTOL
+
+
+def test_walk_ring_self_gravity_visible(orc):
+    """SURVEY.md §7 hard part 4: the central mass hides ring-ring errors; compare with its contribution removed."""
+    n = 20000
+    parts = orc.circular_orbits(n, seed=3)
+    acc, _, oacc, _ = _walk_case(orc, parts)
+    r = parts["p"][1:]
+    d3 = np.linalg.norm(r, axis=1) ** 3
+    central = -r / d3[:, None]
+    a, b = acc[1:] - central, oacc[1:] - central
+    # ring self-gravity is ~1e-9 of the total: 1e-12 of the total is 1e-3 of it; require far better
+    assert (np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)).max() < 1e-6
+    assert rel_err(acc, oacc).max() <= ACC_RTOL
+
+
+@pytest.mark.parametrize("theta", [0.2, 0.3, 0.5, 0.7])
+def test_walk_equal_mass_cube(orc, theta):
+    parts = cube(20000, seed=9)
+    acc, cnt, oacc, ocnt = _walk_case(orc, parts, theta=theta)
+    for k, f in enumerate(("node_visits", "accepts", "leaf_visits", "pp")):
+        assert np.array_equal(cnt[:, k], ocnt[f]), f
+    assert rel_err(acc, oacc).max() <= 1e-11     # heavy cancellation in a uniform cube: |sum| << sum|terms|
+
+
+def test_walk_exact_math_flag(orc):
+    parts = cube(8000, seed=2)
+    acc, _, oacc, _ = _walk_case(orc, parts, flags=kd.FLAG_EXACT_MATH)
+    assert rel_err(acc, oacc).max() <= 1e-13     # same sqrt / divide as the reference; only the summation order differs
+
+
+def test_kick_drift_bit_exact(orc):
+    parts = orc.circular_orbits(30000, seed=8)
+    rng = np.random.default_rng(0)
+    acc = rng.normal(size=(len(parts), 3))
+    with kd.KDTreeSim() as sim:
+        sim.upload(parts)
+        sim.build_tree()
+        sim.set_accel(acc)
+        assert np.array_equal(bits(sim.accel()), bits(acc))
+        sim.kick_drift(1e-3)
+        out = sim.download()
+        assert not sim.accel().any()          # a[k] = 0 (array_kd_tree.rs:659-661)
+    ref = parts.copy()
+    orc.kick_drift(ref, acc.copy(), 1e-3)
+    assert out.tobytes() == ref.tobytes()
+
+
+def test_upload_download_roundtrip(orc):
+    parts = cube(12345, seed=4)
+    with kd.KDTreeSim() as sim:
+        sim.upload(parts)
+        assert sim.download().tobytes() == parts.tobytes()
+
+
+@pytest.mark.parametrize("n,steps", [(1000, 100), (20000, 10)])
+def test_simple_sim_trajectory(orc, n, steps):
+    parts = orc.circular_orbits(n, seed=n)
+    g = parts.copy()
+    kd.simple_sim(g, 1e-3, steps)
+    for order in (ORDER_CANONICAL, ORDER_FAITHFUL):
+        o = parts.copy()
+        orc.simple_sim(o, 1e-3, steps, order=order, seed=3)
+        scale = np.abs(o["p"]).max()
+        assert np.linalg.norm(g["p"] - o["p"], axis=1).max() / scale <= POS_RTOL
+        assert np.linalg.norm(g["v"] - o["v"], axis=1).max() / np.abs(o["v"]).max() <= POS_RTOL
+    assert np.array_equal(g["m"], parts["m"]) and np.array_equal(g["r"], parts["r"])
+
+
+def test_simple_sim_sequential_crate_semantics(orc):
+    """BASELINE config #1: Sequential/RustVersion (MAX_PARTS=7, dense layout), N=1000, 100 steps."""
+    parts = orc.circular_orbits(1000, seed=1)
+    g = parts.copy()
+    with kd.KDTreeSim(max_parts=7, layout=kd.LAYOUT_DENSE) as sim:
+        sim.simple_sim_bodies(g, 1e-3, 100)
+    o = parts.copy()
+    orc.simple_sim(o, 1e-3, 100, max_parts=7, layout=O_DENSE, order=ORDER_FAITHFUL, seed=9, threads=1)
+    assert np.linalg.norm(g["p"] - o["p"], axis=1).max() / np.abs(o["p"]).max() <= POS_RTOL
+
+
+def test_two_bodies_orbit(orc):
+    """Parallel/GoVersion/kdtree_test.go:63-74 (prints only there): half orbit after 1000 steps of pi/1000."""
+    g = kd.two_bodies()
+    kd.simple_sim(g, np.pi / 1000, 1000)
+    gold = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "pure_two_bodies.npz"))
+    after = gold["after"].view(PARTICLE).reshape(-1)
+    assert np.abs(g["p"] - after["p"]).max() <= 1e-12      # against the reference Python's own output
+    assert abs(g["p"][1][0] + 1.0) < 2e-2
+
+
+def test_golden_reference_python_trajectory():
+    """The reference's own PureVersion output (tests/golden): 301 particles, 5 steps."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "pure_ring300_mp8.npz"))
+    parts = gold["parts0"].view(PARTICLE).reshape(-1).copy()
+    acc = kd.calc_accel_all(parts)
+    assert rel_err(acc, gold["acc"]).max() <= ACC_RTOL
+    kd.simple_sim(parts, float(gold["dt"]), int(gold["steps"]))
+    after = gold["after"].view(PARTICLE).reshape(-1)
+    assert np.abs(parts["p"] - after["p"]).max() / np.abs(after["p"]).max() <= POS_RTOL
+
+
+def test_reference_api_mirror(orc):
+    """two_leaves (array_kd_tree.rs:711-731) through the reference-shaped free functions."""
+    parts = kd.circular_orbits(11)
+    nodes = kd.allocate_node_vec(len(parts))
+    idx = np.arange(len(parts), dtype=np.uint64)
+    kd.build_tree_par4(idx, 0, parts, nodes, 1)
+    assert nodes[0]["kind"] == kd.INTERNAL and nodes[1]["kind"] == kd.LEAF and nodes[2]["kind"] == kd.LEAF
+    assert nodes[1]["num_parts"] + nodes[2]["num_parts"] == 12
+    assert sorted(idx.tolist()) == list(range(12))
+    # single_node (array_kd_tree.rs:698-709)
+    two = kd.two_bodies()
+    nodes = kd.allocate_node_vec(2)
+    idx = np.arange(2, dtype=np.uint64)
+    last, nodes = kd.build_tree(idx, 0, 2, two, 0, nodes)
+    assert last == 0 and nodes[0]["kind"] == kd.LEAF and nodes[0]["num_parts"] == 2
+
+
+def test_error_codes_instead_of_panics():
+    with kd.KDTreeSim() as sim:
+        with pytest.raises(kd.KdnbError):
+            sim.build_tree()                     # nothing uploaded
+        sim.upload(kd.circular_orbits(100))
+        with pytest.raises(kd.KdnbError):
+            sim.calc_accel()                     # no tree yet
+        sim.build_tree()
+        sim.calc_accel()
+        sim.kick_drift(1e-3)
+        with pytest.raises(kd.KdnbError):
+            sim.calc_accel()                     # tree is stale after the drift
+    with pytest.raises(kd.KdnbError):
+        kd.KDTreeSim(max_parts=3)
+
+
+def test_big_solar_with_steps_invariant(orc):
+    """array_kd_tree.rs:816-832 — 10 steps, rebuild, the partition invariant still holds."""
+    parts = orc.circular_orbits(5000, seed=6)
+    with kd.KDTreeSim() as sim:
+        sim.upload(parts)
+        sim.simple_sim(1e-3, 10)
+        sim.build_tree()
+        nodes, idx = sim.tree()
+        moved = sim.download()
+    assert orc.check_tree_struct(to_oracle_nodes(orc, nodes, idx, 8), moved) == 0
+
+
+def test_full_size_properties_1m(orc):
+    """BASELINE config #3 size (N=1,000,000): size-independent properties + a sampled oracle comparison."""
+    n = 1_000_000
+    parts = orc.circular_orbits(n, seed=12345)
+    with kd.KDTreeSim(flags=kd.FLAG_WALK_COUNTS) as sim:
+        sim.upload(parts)
+        sim.build_tree()
+        nodes, idx = sim.tree()
+        sim.calc_accel()
+        acc = sim.accel()
+        cnt = sim.walk_counts()
+    assert len(nodes) == 524287
+    assert np.array_equal(np.sort(idx), np.arange(n + 1, dtype=np.uint64))              # indices is a permutation
+    used = nodes[(nodes["kind"] == kd.INTERNAL) | (nodes["num_parts"] > 0)]
+    assert len(used) == 262143 and nodes["num_parts"].sum() == n + 1
+    onodes = to_oracle_nodes(orc, nodes, idx, 8)
+    assert orc.check_tree_struct(onodes, parts) == 0
+    # tree bit-exact against the canonical oracle at full size
+    cn, cidx, _ = orc.build_tree_canonical(parts, threads=8)
+    assert_tree_bit_exact(orc, nodes, idx, cn, cidx, 8)
+    # walk: all particles against the oracle (OpenMP), decisions exact
+    oacc, ocnt = orc.calc_accel_all(parts, onodes, counts=True)
+    assert rel_err(acc, oacc).max() <= ACC_RTOL
+    for k, f in enumerate(("node_visits", "accepts", "leaf_visits", "pp")):
+        assert np.array_equal(cnt[:, k], ocnt[f]), f
