@@ -16,6 +16,7 @@ constexpr int LVL_CHUNK = 2048;  // list entries per CTA in the global-level par
 struct Ctx {
   // configuration
   int device = 0;
+  int num_sms = 148;
   uint32_t mp = 8;
   int layout = KDNB_LAYOUT_PADDED;
   double theta = 0.3, theta2 = 0.09;

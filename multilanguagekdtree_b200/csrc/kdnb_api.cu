@@ -111,7 +111,7 @@ static void free_all(Ctx* c) {
   fr(c->ms);
   fr(c->perm);
   fr(c->rank);
-  fr(c->posm);
+  c->posm = nullptr;  // lives inside the nodes allocation
   fr(c->acc_t);
   fr(c->wcounts);
   fr(c->tmp3);
@@ -161,11 +161,11 @@ static int plan(Ctx* c, uint64_t n) {
     if (!rc) rc = dev_alloc(c, &c->tmid, table);
     if (!rc) rc = dev_alloc(c, &c->tsd, table);
     if (!rc) rc = dev_alloc(c, &c->chunk_cnt, chunks);
-    if (!rc) rc = dev_alloc(c, &c->nodes, c->n_nodes);
+    if (!rc) rc = dev_alloc(c, &c->nodes, c->n_nodes + (n + 1) / 2 + 1);  // node records, then the tree-ordered particles (one pool: walk.cu)
     if (!rc) rc = dev_alloc(c, &c->ms, c->n_nodes);
     if (!rc) rc = dev_alloc(c, &c->perm, n);
     if (!rc) rc = dev_alloc(c, &c->rank, n);
-    if (!rc) rc = dev_alloc(c, &c->posm, n);
+    if (!rc) c->posm = reinterpret_cast<PosM*>(c->nodes + c->n_nodes);
     if (!rc) rc = dev_alloc(c, &c->acc_t, 3 * padded_slots(n));
     if (!rc && (c->flags & KDNB_FLAG_WALK_COUNTS)) rc = dev_alloc(c, &c->wcounts, 4 * n);
     if (!rc) rc = dev_alloc(c, &c->tmp3, 4 * n);
@@ -176,6 +176,7 @@ static int plan(Ctx* c, uint64_t n) {
       return rc;
     }
   }
+  c->posm = reinterpret_cast<PosM*>(c->nodes + c->n_nodes);
   if (grow || c->planned_n != n) {
     KDNB_CUDA_TRY(c, cudaMemsetAsync(c->acc_t, 0, 3 * padded_slots(n) * sizeof(double), c->stream));
     init_unused_nodes(c);  // slots the build never writes keep the reference's default Leaf{0, NEGS}
@@ -273,6 +274,7 @@ kdnb_ctx* kdnb_create(const kdnb_config* cfg) {
     delete h;
     return nullptr;
   }
+  cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
   return h;
 }
 
