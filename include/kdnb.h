@@ -126,6 +126,8 @@ uint64_t kdnb_node_count(const kdnb_ctx* ctx); /* allocate_node_vec(count).len()
 
 /* ---- multi-GPU (new; the reference is single-process).  Tree replicated, walk sharded by tree-ordered
  * ranges, tree-ordered accelerations exchanged with one ncclAllGather per step. */
+/* pure: the tree-slot range [begin, end) rank `rank` of `world_size` walks for `count` particles (warp-aligned shards) */
+int kdnb_shard_range(uint64_t count, int rank, int world_size, uint64_t* begin, uint64_t* end);
 int kdnb_comm_unique_id(void* id_out_128_bytes);
 int kdnb_comm_init(kdnb_ctx* ctx, const void* id_128_bytes, int rank, int world_size);
 

@@ -34,6 +34,15 @@ def allocate_node_vec(num_parts: int, max_parts: int = MAX_PARTS) -> np.ndarray:
     return nodes
 
 
+def shard_range(count: int, rank: int, world: int):
+    """Tree-slot range [begin, end) that rank `rank` of `world` walks (kdnb_shard_range; pure, needs no GPU)."""
+    b, e = C.c_uint64(0), C.c_uint64(0)
+    rc = _lib.load().kdnb_shard_range(count, rank, world, C.byref(b), C.byref(e))
+    if rc != 0:
+        raise KdnbError(f"kdnb_shard_range rc={rc}")
+    return int(b.value), int(e.value)
+
+
 class KDTreeSim:
     """One GPU context: owns what `simple_sim` owns (acc, tree, indices; array_kd_tree.rs:624-630)."""
 

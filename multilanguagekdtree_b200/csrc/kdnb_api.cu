@@ -117,7 +117,9 @@ static void free_all(Ctx* c) {
   fr(c->tmp3);
 }
 
-static uint64_t padded_slots(uint64_t n) { return n + 32ull * 64ull; }
+static uint64_t padded_slots(uint64_t n) { return n + 64ull * 64ull; }
+// tree slots per rank: equal, warp-group aligned (64 = 32 lanes x 2 particles per lane) so that shards never split a warp
+static uint64_t shard_slots_for(uint64_t n, int world) { return (((n + world - 1) / world) + 63) / 64 * 64; }
 
 // (re)plan and (re)allocate for `n` particles
 static int plan(Ctx* c, uint64_t n) {
@@ -182,7 +184,7 @@ static int plan(Ctx* c, uint64_t n) {
     init_unused_nodes(c);  // slots the build never writes keep the reference's default Leaf{0, NEGS}
     c->planned_n = n;
   }
-  if (c->world > 1) c->shard_slots = (((n + c->world - 1) / c->world) + 31) / 32 * 32;
+  if (c->world > 1) c->shard_slots = shard_slots_for(n, c->world);
   return 0;
 }
 
@@ -430,6 +432,14 @@ uint64_t kdnb_nodes_needed(uint64_t num_parts, uint32_t max_parts) {
 
 uint64_t kdnb_node_count(const kdnb_ctx* ctx) { return ctx ? ctx->c.n_nodes : 0; }
 
+int kdnb_shard_range(uint64_t count, int rank, int world_size, uint64_t* begin, uint64_t* end) {
+  if (world_size < 1 || rank < 0 || rank >= world_size || !begin || !end) return KDNB_E_INVALID;
+  const uint64_t shard = shard_slots_for(count, world_size);
+  *begin = std::min<uint64_t>(count, (uint64_t)rank * shard);
+  *end = std::min<uint64_t>(count, (uint64_t)(rank + 1) * shard);
+  return 0;
+}
+
 int kdnb_comm_unique_id(void* id_out) {
   std::string why;
   if (!id_out || !load_nccl(&why)) {
@@ -462,7 +472,7 @@ int kdnb_comm_init(kdnb_ctx* ctx, const void* id_bytes, int rank, int world_size
   c->nccl_comm = comm;
   c->rank_id = rank;
   c->world = world_size;
-  if (c->n) c->shard_slots = (((c->n + c->world - 1) / c->world) + 31) / 32 * 32;
+  if (c->n) c->shard_slots = shard_slots_for(c->n, c->world);
   return 0;
 }
 
