@@ -1,37 +1,40 @@
 // walk.cu — theta-criterion force walk, calc_accel / accel_recur of the reference
 // (Parallel/RustVersion/src/array_kd_tree.rs:585-621) with calc_pp_accel (array_particle.rs:67-76) in the leaves.
 //
-// Mapping: one warp = 32*PPL consecutive TREE-ORDERED particles (spatially compact: 4-7 adjacent leaves per 32),
-// PPL particles per lane.  The warp walks the tree once with a shared-memory stack of (node, lane masks) entries:
-//   * every lane in the entry's mask evaluates the reference's acceptance test for ITS OWN particle(s),
+// One warp owns 32*PPL consecutive TREE-ORDERED particles (a compact patch of ~10 leaves), PPL per lane, and keeps a
+// shared-memory stack of frontier entries (node, one lane mask per 32 particles).  Per round it pops up to 32
+// entries and classifies them ONE NODE PER LANE against the bounding box of its particles:
+//   far   : size^2 <  theta^2 * dmin^2 * (1 - 1e-9)  -> every particle in the entry's masks accepts the node
+//   near  : size^2 >= theta^2 * dmax^2 * (1 + 1e-9)  -> every particle opens it: both children are pushed
+//   mixed : otherwise, and leaves                    -> handled one node at a time by the whole warp
+// dmin/dmax are the distances from the node's centre of mass to the box; the 1e-9 margin dwarfs the <= 1e-15
+// rounding of either side, so "far"/"near" provably agree with the reference's per-particle test
 //       size*size < (THETA*THETA) * dist_sqr            (array_kd_tree.rs:606)
-//     with the same unfused operation order, so each particle accepts / opens exactly the nodes the
-//     reference does (checked by the per-particle visit counters, KDNB_FLAG_WALK_COUNTS);
-//   * an accepted node is NOT evaluated on the spot: its monopole {cm, m} and the masks of accepting lanes are
-//     appended to a per-warp interaction list in shared memory; if any lane still has to open the node
-//     (__ballot_sync) both children are pushed with the remaining masks;
-//   * a leaf appends its particles (loaded by up to MAX_PARTS lanes in one coalesced access) with the masks of
-//     lanes that reached it, minus the lane that owns the particle (leaf_parts[i] != p, :590);
-//   * when the list is full it is drained: all lanes stream over the point masses (shared-memory broadcast loads,
-//     no global loads, no divergent control flow) and accumulate -m * d / r^3 under their mask bit.
-// Traversal (latency-bound pointer chasing, 10 FP64 ops per test) and force evaluation (FP64-pipe-bound, 16 ops
-// per interaction, unrolled) are thereby decoupled.  Node records are one 64-byte line; every node load is
-// warp-uniform.
-// Accumulation is a running f64 sum per particle (the reference combines pairwise along the recursion, :611-613;
-// the difference is summation order only and is covered by the stated 1e-12 tolerance).
+// For a mixed node every lane evaluates exactly that test for its own particles, with the reference's unfused
+// operation order, and __ballot_sync splits the masks into accepted and still-open lanes.  Every particle thus
+// accepts / opens precisely the nodes the reference's recursion does (checked by KDNB_FLAG_WALK_COUNTS against the
+// oracle: per-particle counts of tests, accepts, leaf visits and pair interactions are identical).
 //
-// Tried and rejected on the GPU (profiles/README.md): per-lane interaction queues with gathered record loads
-// (L1-bound, 5.8 ms vs 4.7 ms at N=1M) and persistent CTAs with static contiguous ranges (tail imbalance).
+// Forces are not evaluated during the traversal: accepted monopoles {cm, m} and leaf particles (minus the lane that
+// owns the particle: leaf_parts[i] != p, :590) are appended with their lane mask to a per-warp, per-32-particle
+// interaction list in shared memory, which is drained by a branch-free, 4-way unrolled loop: 16 FP64 instructions
+// per interaction, broadcast shared-memory loads, no global loads.  About 3/4 of the nodes a warp touches are
+// far / near (profiles/README.md), so the serial per-node work — which dominated the first versions of this kernel —
+// shrinks to the mixed nodes, and the drain loop runs on lists that skip 32-particle halves nobody in them needs.
+//
+// Accumulation is a running f64 sum per particle (the reference combines pairwise along the recursion, :611-613);
+// the difference is summation order only and is covered by the stated 1e-12 tolerance.
 #include <cstdlib>
 
 #include "ctx.cuh"
 
 namespace kdnb {
 
-constexpr int WALK_THREADS = 128;
+constexpr int WALK_THREADS = 64;
 constexpr int WALK_WARPS = WALK_THREADS / 32;
-constexpr int WALK_STACK = 40;  // deepest stack = tree depth + 2 (<= 27 at 1e8 particles)
-constexpr int WALK_LIST = 64;   // interaction-list capacity per warp (>= 2 * largest MAX_PARTS)
+constexpr int WALK_STACK = 320;  // soft capacity: batches shrink as the stack fills (see nb below)
+constexpr int WALK_SLACK = 32;   // depth-first tail when the stack is at capacity (tree depth <= 27 at 1e8 particles)
+constexpr int WALK_LIST = 64;    // interaction-list capacity per 32 particles (>= 32 + largest MAX_PARTS)
 
 struct __align__(32) Rec32 {
   double a, b, c, d;
@@ -51,13 +54,12 @@ __device__ __forceinline__ double neg_m_over_r3_fast(double mneg, double d2) {
   return fma(__dmul_rn(mq, e), q, mq);
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 template <int PPL>
 struct WalkSmem {
-  uint4 stk[WALK_WARPS][WALK_STACK];   // {node, mask0, mask1, -}
-  Rec32 lpos[WALK_WARPS][WALK_LIST];   // {x, y, z, m} of a monopole or of a leaf particle
-  uint4 lmask[WALK_WARPS][WALK_LIST];  // {mask0, mask1, is_particle, -}
+  uint32_t snode[WALK_WARPS][WALK_STACK + WALK_SLACK];
+  uint32_t smask[WALK_WARPS][PPL][WALK_STACK + WALK_SLACK];
+  Rec32 lpos[WALK_WARPS][PPL][WALK_LIST];   // {x, y, z, m} of a monopole or of a leaf particle
+  uint2 lmask[WALK_WARPS][PPL][WALK_LIST];  // {lane mask, is_particle}
 };
 
 template <bool EXACT>
@@ -85,144 +87,254 @@ __device__ __forceinline__ void interact(const Rec32& e, bool use, bool is_parti
   }
 }
 
-template <int PPL, bool EXACT, bool COUNTS>
-__device__ __forceinline__ void drain_list(const Rec32* __restrict__ lpos, const uint4* __restrict__ lmask, int cnt,
-                                           int lane, const double (&px)[PPL], const double (&py)[PPL],
-                                           const double (&pz)[PPL], double (&ax)[PPL], double (&ay)[PPL],
-                                           double (&az)[PPL], unsigned long long (&cp)[PPL]) {
-#pragma unroll 2
+// all lanes stream over one 32-particle list
+template <bool EXACT, bool COUNTS>
+__device__ __forceinline__ void drain_list(const Rec32* __restrict__ lpos, const uint2* __restrict__ lmask, int cnt,
+                                           int lane, double px, double py, double pz, double& ax, double& ay,
+                                           double& az, unsigned long long& cp) {
+  __syncwarp();
+#pragma unroll 4
   for (int i = 0; i < cnt; ++i) {
     const Rec32 e = lpos[i];
-    const uint4 mk = lmask[i];
-#pragma unroll
-    for (int u = 0; u < PPL; ++u) {
-      const uint32_t m = (u == 0 ? mk.x : mk.y);
-      const bool use = (m >> lane) & 1u;
-      interact<EXACT>(e, use, mk.z != 0, px[u], py[u], pz[u], ax[u], ay[u], az[u]);
-      if (COUNTS) cp[u] += (use && mk.z) ? 1 : 0;
-    }
+    const uint2 mk = lmask[i];
+    const bool use = (mk.x >> lane) & 1u;
+    interact<EXACT>(e, use, mk.y != 0, px, py, pz, ax, ay, az);
+    if (COUNTS) cp += (use && mk.y) ? 1 : 0;
   }
+  __syncwarp();
 }
 
-template <int PPL, int MINB, bool PF, bool EXACT, bool COUNTS>
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+enum : int { K_NONE = 0, K_FAR = 1, K_NEAR = 2, K_SERIAL = 3 };
+
+template <int PPL, int MINB, bool EXACT, bool COUNTS>
 __global__ void __launch_bounds__(WALK_THREADS, MINB)
 walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, double* __restrict__ acc_t,
-            uint32_t slot_begin, uint32_t slot_end, double theta2, uint32_t max_parts,
-            unsigned long long* __restrict__ wcounts) {
+            uint32_t slot_begin, uint32_t slot_end, double theta2, unsigned long long* __restrict__ wcounts) {
   __shared__ WalkSmem<PPL> S;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
   const uint32_t base = slot_begin + (blockIdx.x * WALK_WARPS + w) * (32 * PPL);
-  uint32_t slot[PPL], mask[PPL];
+  uint32_t slot[PPL], mk[PPL];
+  int ln[PPL];
   double px[PPL], py[PPL], pz[PPL], ax[PPL], ay[PPL], az[PPL];
   unsigned long long cv[PPL], ca[PPL], cl[PPL], cp[PPL];
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  uint32_t* snode = S.snode[w];
 #pragma unroll
   for (int u = 0; u < PPL; ++u) {
     slot[u] = base + u * 32 + lane;
     const bool valid = slot[u] < slot_end;
-    mask[u] = __ballot_sync(0xffffffffu, valid);
+    const uint32_t m0 = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) S.smask[w][u][0] = m0;
     px[u] = py[u] = pz[u] = 0.0;
     if (valid) {
       const PosM me = posm[slot[u]];
       px[u] = me.x;
       py[u] = me.y;
       pz[u] = me.z;
+      lo[0] = fmin(lo[0], me.x), hi[0] = fmax(hi[0], me.x);
+      lo[1] = fmin(lo[1], me.y), hi[1] = fmax(hi[1], me.y);
+      lo[2] = fmin(lo[2], me.z), hi[2] = fmax(hi[2], me.z);
     }
     ax[u] = ay[u] = az[u] = 0.0;
     cv[u] = ca[u] = cl[u] = cp[u] = 0;
+    ln[u] = 0;
   }
-  if (mask[0] == 0) return;
+  if (base >= slot_end) return;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    lo[k] = warp_min(lo[k]);
+    hi[k] = warp_max(hi[k]);
+  }
+  if (lane == 0) snode[0] = 0;
+  __syncwarp();
+  const double far_margin = 1.0 - 1e-9, near_margin = 1.0 + 1e-9;
 
-  uint4* st = S.stk[w];
-  Rec32* lpos = S.lpos[w];
-  uint4* lmask = S.lmask[w];
-  int sp = 0, ln = 0;
-  uint32_t node = 0;  // the root, with every valid lane in the masks
-  bool more = true;
-  while (more) {
-    const Rec32* rec = reinterpret_cast<const Rec32*>(nodes + node);
-    const Rec32 c = rec[0];                                           // cx, cy, cz, m
-    const int4 info = __ldg(reinterpret_cast<const int4*>(rec + 1));  // size2, (a, b)
-    if (PF) prefetch_l1(rec + 2);  // the left child is the next record
-    const uint32_t na = (uint32_t)info.z, nb = (uint32_t)info.w;
-    bool descend = false;
-    bool in[PPL];
+  int sp = 1;
+  while (sp > 0) {
+    // ---- pop a batch: lane l takes entry sp+l after the pop (order inside a batch is irrelevant)
+    const int room = WALK_STACK - sp;
+    const int nb = min(min(sp, 32), max(1, room));
+    sp -= nb;
+    const bool has = lane < nb;
+    uint32_t node = 0, na = 0, nbits = 0;
+    int kind = K_NONE;
+    Rec32 c;
+    c.a = c.b = c.c = c.d = 0.0;
 #pragma unroll
-    for (int u = 0; u < PPL; ++u) in[u] = (mask[u] >> lane) & 1u;
-    if (nb & WN_INTERNAL) {
-      const double size2 = __hiloint2double(info.y, info.x);
-      uint32_t am[PPL], any = 0, open_any = 0;
+    for (int u = 0; u < PPL; ++u) mk[u] = 0;
+    if (has) {
+      node = snode[sp + lane];
 #pragma unroll
-      for (int u = 0; u < PPL; ++u) {
-        const double dx = __dsub_rn(px[u], c.a), dy = __dsub_rn(py[u], c.b), dz = __dsub_rn(pz[u], c.c);
-        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));  // :604
-        const bool accept = in[u] && (size2 < __dmul_rn(theta2, d2));                                     // :606
-        am[u] = __ballot_sync(0xffffffffu, accept);
-        any |= am[u];
-        mask[u] &= ~am[u];
-        open_any |= mask[u];
-        if (COUNTS) {
-          cv[u] += in[u];
-          ca[u] += accept;
+      for (int u = 0; u < PPL; ++u) mk[u] = S.smask[w][u][sp + lane];
+      const Rec32* rec = reinterpret_cast<const Rec32*>(nodes + node);
+      const int4 info = __ldg(reinterpret_cast<const int4*>(rec + 1));  // size2, (a, b)
+      na = (uint32_t)info.z;
+      nbits = (uint32_t)info.w;
+      kind = K_SERIAL;
+      if (nbits & WN_INTERNAL) {
+        c = rec[0];  // cx, cy, cz, m
+        const double size2 = __hiloint2double(info.y, info.x);
+        double dmin2 = 0.0, dmax2 = 0.0;
+        const double cc[3] = {c.a, c.b, c.c};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double below = lo[k] - cc[k], above = cc[k] - hi[k];  // > 0 when the centre is outside the box
+          const double dn = fmax(0.0, fmax(below, above));
+          const double df = fmax(fabs(below), fabs(above));  // = max(|c-lo|, |c-hi|)
+          dmin2 = fma(dn, dn, dmin2);
+          dmax2 = fma(df, df, dmax2);
         }
+        if (size2 < theta2 * dmin2 * far_margin) kind = K_FAR;
+        else if (size2 >= theta2 * dmax2 * near_margin) kind = K_NEAR;
       }
-      if (any) {
-        if (lane == 0) {
-          lpos[ln] = c;
-          lmask[ln] = make_uint4(am[0], PPL > 1 ? am[PPL - 1] : 0u, 0u, 0u);
-        }
-        ln += 1;
-      }
-      descend = open_any != 0;
-      if (descend) {
-        st[sp++] = make_uint4(na, mask[0], PPL > 1 ? mask[PPL - 1] : 0u, 0u);  // right child waits on the stack
-        if (PF) prefetch_l1(nodes + na);
-        node = node + 1;  // left child first, as the recursion (:611): it is the next record, masks stay in registers
-      }
-    } else {
-      const uint32_t cnt = nb;
-      if (COUNTS) {
-#pragma unroll
-        for (int u = 0; u < PPL; ++u) cl[u] += in[u];
-      }
-      if ((uint32_t)lane < cnt) {
-        const uint32_t j = na + lane;
-        const PosM q = posm[j];
-        Rec32 r;
-        r.a = q.x;
-        r.b = q.y;
-        r.c = q.z;
-        r.d = q.m;
-        uint32_t mk[PPL];
+    }
+    __syncwarp();
+    if (COUNTS) {  // every particle in an entry's mask tests that node (and accepts it when it is far)
+      for (int s = 0; s < nb; ++s) {
+        const int ks = __shfl_sync(0xffffffffu, kind, s);
+        const uint32_t nbs = __shfl_sync(0xffffffffu, nbits, s);
 #pragma unroll
         for (int u = 0; u < PPL; ++u) {
-          const uint32_t t = j - (base + u * 32);  // the lane that owns particle j, if it is one of ours
-          mk[u] = t < 32u ? (mask[u] & ~(1u << t)) : mask[u];
+          const uint32_t ms = __shfl_sync(0xffffffffu, mk[u], s);
+          const unsigned long long bit = (ms >> lane) & 1u;
+          if (ks == K_FAR || ks == K_NEAR) cv[u] += bit;
+          if (ks == K_FAR) ca[u] += bit;
+          if (ks == K_SERIAL && !(nbs & WN_INTERNAL)) cl[u] += bit;
         }
-        lpos[ln + lane] = r;
-        lmask[ln + lane] = make_uint4(mk[0], PPL > 1 ? mk[PPL - 1] : 0u, 1u, 0u);
-      }
-      ln += cnt;
-    }
-    if (ln + (int)max_parts > WALK_LIST) {
-      __syncwarp();
-      drain_list<PPL, EXACT, COUNTS>(lpos, lmask, ln, lane, px, py, pz, ax, ay, az, cp);
-      __syncwarp();
-      ln = 0;
-    }
-    if (!descend) {
-      more = sp > 0;
-      if (more) {
-        const uint4 e = st[--sp];
-        node = e.x;
-        mask[0] = e.y;
-        if (PPL > 1) mask[PPL - 1] = e.z;
       }
     }
+    // ---- far nodes: append the monopole to the lists of the 32-particle halves that hold accepting particles
+    if (__any_sync(0xffffffffu, kind == K_FAR)) {
+#pragma unroll
+      for (int u = 0; u < PPL; ++u) {
+        const bool mine = kind == K_FAR && mk[u] != 0;
+        const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+        const int add = __popc(bal);
+        if (ln[u] + add > WALK_LIST) {
+          drain_list<EXACT, COUNTS>(S.lpos[w][u], S.lmask[w][u], ln[u], lane, px[u], py[u], pz[u], ax[u], ay[u], az[u], cp[u]);
+          ln[u] = 0;
+        }
+        if (mine) {
+          const int i = ln[u] + __popc(bal & lt);
+          S.lpos[w][u][i] = c;
+          S.lmask[w][u][i] = make_uint2(mk[u], 0u);
+        }
+        ln[u] += add;
+      }
+    }
+    // ---- near nodes: push both children with the same masks
+    {
+      const uint32_t bal = __ballot_sync(0xffffffffu, kind == K_NEAR);
+      if (kind == K_NEAR) {
+        const int i = sp + 2 * __popc(bal & lt);
+        snode[i] = na;            // right
+        snode[i + 1] = node + 1;  // left (the next record)
+#pragma unroll
+        for (int u = 0; u < PPL; ++u) {
+          S.smask[w][u][i] = mk[u];
+          S.smask[w][u][i + 1] = mk[u];
+        }
+      }
+      sp += 2 * __popc(bal);
+    }
+    // ---- leaves and mixed nodes: one at a time, all lanes
+    uint32_t ser = __ballot_sync(0xffffffffu, kind == K_SERIAL);
+    while (ser) {
+      const int src = __ffs(ser) - 1;
+      ser &= ser - 1;
+      const uint32_t nd = __shfl_sync(0xffffffffu, node, src);
+      const uint32_t a_s = __shfl_sync(0xffffffffu, na, src);
+      const uint32_t b_s = __shfl_sync(0xffffffffu, nbits, src);
+      uint32_t ms[PPL];
+#pragma unroll
+      for (int u = 0; u < PPL; ++u) ms[u] = __shfl_sync(0xffffffffu, mk[u], src);
+      if (!(b_s & WN_INTERNAL)) {
+        // leaf: its particles go to the lists with the masks of the lanes that reached it, minus the owner (:590)
+        const int cnt = (int)b_s;
+        Rec32 r;
+        r.a = r.b = r.c = r.d = 0.0;
+        const uint32_t j = a_s + lane;
+        if (lane < cnt) {
+          const PosM q = posm[j];
+          r.a = q.x, r.b = q.y, r.c = q.z, r.d = q.m;
+        }
+#pragma unroll
+        for (int u = 0; u < PPL; ++u) {
+          if (ms[u] == 0) continue;
+          if (ln[u] + cnt > WALK_LIST) {
+            drain_list<EXACT, COUNTS>(S.lpos[w][u], S.lmask[w][u], ln[u], lane, px[u], py[u], pz[u], ax[u], ay[u], az[u], cp[u]);
+            ln[u] = 0;
+          }
+          if (lane < cnt) {
+            const uint32_t t = j - (base + u * 32);  // the lane that owns particle j, if it is one of ours
+            const uint32_t m = t < 32u ? (ms[u] & ~(1u << t)) : ms[u];
+            S.lpos[w][u][ln[u] + lane] = r;
+            S.lmask[w][u][ln[u] + lane] = make_uint2(m, 1u);
+          }
+          ln[u] += cnt;
+        }
+      } else {
+        // mixed node: the reference's test, per particle (array_kd_tree.rs:601-606)
+        const Rec32* rec = reinterpret_cast<const Rec32*>(nodes + nd);
+        const Rec32 cs = rec[0];
+        const double size2 = __ldg(reinterpret_cast<const double*>(rec + 1));
+        uint32_t open_any = 0;
+#pragma unroll
+        for (int u = 0; u < PPL; ++u) {
+          const bool in = (ms[u] >> lane) & 1u;
+          const double dx = __dsub_rn(px[u], cs.a), dy = __dsub_rn(py[u], cs.b), dz = __dsub_rn(pz[u], cs.c);
+          const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));  // :604
+          const bool accept = in && (size2 < __dmul_rn(theta2, d2));                                        // :606
+          const uint32_t am = __ballot_sync(0xffffffffu, accept);
+          if (COUNTS) {
+            cv[u] += in;
+            ca[u] += accept;
+          }
+          ms[u] &= ~am;
+          open_any |= ms[u];
+          if (am) {
+            if (ln[u] + 1 > WALK_LIST) {
+              drain_list<EXACT, COUNTS>(S.lpos[w][u], S.lmask[w][u], ln[u], lane, px[u], py[u], pz[u], ax[u], ay[u], az[u], cp[u]);
+              ln[u] = 0;
+            }
+            if (lane == 0) {
+              S.lpos[w][u][ln[u]] = cs;
+              S.lmask[w][u][ln[u]] = make_uint2(am, 0u);
+            }
+            ln[u] += 1;
+          }
+        }
+        if (open_any) {
+          if (lane == 0) {
+            snode[sp] = a_s;         // right
+            snode[sp + 1] = nd + 1;  // left
+#pragma unroll
+            for (int u = 0; u < PPL; ++u) {
+              S.smask[w][u][sp] = ms[u];
+              S.smask[w][u][sp + 1] = ms[u];
+            }
+          }
+          sp += 2;
+        }
+      }
+    }
+    __syncwarp();
   }
-  __syncwarp();
-  drain_list<PPL, EXACT, COUNTS>(lpos, lmask, ln, lane, px, py, pz, ax, ay, az, cp);
 #pragma unroll
   for (int u = 0; u < PPL; ++u) {
+    drain_list<EXACT, COUNTS>(S.lpos[w][u], S.lmask[w][u], ln[u], lane, px[u], py[u], pz[u], ax[u], ay[u], az[u], cp[u]);
     if (slot[u] < slot_end) {
       acc_t[3ull * slot[u] + 0] = ax[u];
       acc_t[3ull * slot[u] + 1] = ay[u];
@@ -237,21 +349,21 @@ walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, doub
   }
 }
 
-template <int PPL, int MINB, bool PF>
+template <int PPL, int MINB>
 static void launch_walk(Ctx* c, uint32_t begin, uint32_t end) {
   const uint32_t groups = (end - begin + 32 * PPL - 1) / (32 * PPL);
   const uint32_t grid = (groups + WALK_WARPS - 1) / WALK_WARPS;
   const bool counts = (c->flags & KDNB_FLAG_WALK_COUNTS) != 0;
   const bool exact = (c->flags & KDNB_FLAG_EXACT_MATH) != 0;
-#define KDNB_WALK_ARGS c->nodes, c->posm, c->acc_t, begin, end, c->theta2, c->mp, c->wcounts
+#define KDNB_WALK_ARGS c->nodes, c->posm, c->acc_t, begin, end, c->theta2, c->wcounts
   if (exact && counts)
-    KDNB_LAUNCH(c, (walk_kernel<PPL, MINB, PF, true, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
+    KDNB_LAUNCH(c, (walk_kernel<PPL, 1, true, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
   else if (exact)
-    KDNB_LAUNCH(c, (walk_kernel<PPL, MINB, PF, true, false>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
+    KDNB_LAUNCH(c, (walk_kernel<PPL, 1, true, false>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
   else if (counts)
-    KDNB_LAUNCH(c, (walk_kernel<PPL, MINB, PF, false, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
+    KDNB_LAUNCH(c, (walk_kernel<PPL, 1, false, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
   else
-    KDNB_LAUNCH(c, (walk_kernel<PPL, MINB, PF, false, false>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
+    KDNB_LAUNCH(c, (walk_kernel<PPL, MINB, false, false>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
 #undef KDNB_WALK_ARGS
 }
 
@@ -264,22 +376,17 @@ int walk(Ctx* c) {
   }
   if (end > begin) {
     static const int cfg = [] {
-      const char* s = getenv("KDNB_WALK_CFG");  // tuning knob for profiling runs: <ppl><min blocks per SM>
+      const char* s = getenv("KDNB_WALK_CFG");  // tuning knob for profiling runs: <ppl><min CTAs per SM>
       return s ? atoi(s) : 0;
     }();
     switch (cfg) {
-      case 14: launch_walk<1, 4, false>(c, begin, end); break;
-      case 18: launch_walk<1, 8, false>(c, begin, end); break;
-      case 110: launch_walk<1, 10, false>(c, begin, end); break;
-      case 112: launch_walk<1, 12, false>(c, begin, end); break;
-      case 24: launch_walk<2, 4, false>(c, begin, end); break;
-      case 26: launch_walk<2, 6, false>(c, begin, end); break;
-      case 27: launch_walk<2, 7, false>(c, begin, end); break;
-      case 28: launch_walk<2, 8, false>(c, begin, end); break;
-      case 210: launch_walk<2, 10, false>(c, begin, end); break;
-      case 127: launch_walk<2, 7, true>(c, begin, end); break;
-      case 118: launch_walk<1, 8, true>(c, begin, end); break;
-      default: launch_walk<2, 7, true>(c, begin, end); break;
+      case 18: launch_walk<1, 8>(c, begin, end); break;
+      case 112: launch_walk<1, 12>(c, begin, end); break;
+      case 116: launch_walk<1, 16>(c, begin, end); break;
+      case 28: launch_walk<2, 8>(c, begin, end); break;
+      case 210: launch_walk<2, 10>(c, begin, end); break;
+      case 212: launch_walk<2, 12>(c, begin, end); break;
+      default: launch_walk<1, 12>(c, begin, end); break;
     }
     KDNB_CHECK_LAUNCH(c);
   }
