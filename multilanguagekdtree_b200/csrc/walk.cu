@@ -93,13 +93,74 @@ __device__ __forceinline__ void drain_list(const Rec32* __restrict__ lpos, const
                                            int lane, double px, double py, double pz, double& ax, double& ay,
                                            double& az, unsigned long long& cp) {
   __syncwarp();
-#pragma unroll 4
-  for (int i = 0; i < cnt; ++i) {
-    const Rec32 e = lpos[i];
-    const uint2 mk = lmask[i];
-    const bool use = (mk.x >> lane) & 1u;
-    interact<EXACT>(e, use, mk.y != 0, px, py, pz, ax, ay, az);
-    if (COUNTS) cp += (use && mk.y) ? 1 : 0;
+  if (EXACT || COUNTS) {
+    for (int i = 0; i < cnt; ++i) {
+      const Rec32 e = lpos[i];
+      const uint2 mk = lmask[i];
+      const bool use = (mk.x >> lane) & 1u;
+      interact<EXACT>(e, use, mk.y != 0, px, py, pz, ax, ay, az);
+      if (COUNTS) cp += (use && mk.y) ? 1 : 0;
+    }
+  } else {
+    // DW interactions in lock-step: the FP64 chain of one interaction is ~11 instructions deep, so the independent
+    // chains are interleaved by hand, stage by stage (left to the compiler they were emitted one after another and
+    // the FP64 pipe idled on its own latency: profiles/README.md).  The list is padded to a multiple of DW with
+    // masked-out entries.
+    constexpr int DW = 4;
+    const int padded = (cnt + DW - 1) / DW * DW;
+    if (lane < padded - cnt) {
+      Rec32 z;
+      z.a = z.b = z.c = z.d = 0.0;
+      const_cast<Rec32*>(lpos)[cnt + lane] = z;
+      const_cast<uint2*>(lmask)[cnt + lane] = make_uint2(0u, 0u);
+    }
+    __syncwarp();
+    for (int i = 0; i < padded; i += DW) {
+      double dx[DW], dy[DW], dz[DW], d2[DW], y[DW], y2[DW], ee[DW], mq[DW], q[DW];
+      bool use[DW];
+#pragma unroll
+      for (int j = 0; j < DW; ++j) {
+        const Rec32 e = lpos[i + j];
+        use[j] = (lmask[i + j].x >> lane) & 1u;
+        dx[j] = __dsub_rn(px, e.a);
+        dy[j] = __dsub_rn(py, e.b);
+        dz[j] = __dsub_rn(pz, e.c);
+        mq[j] = -e.d;
+      }
+#pragma unroll
+      for (int j = 0; j < DW; ++j) d2[j] = __dmul_rn(dx[j], dx[j]);
+#pragma unroll
+      for (int j = 0; j < DW; ++j) d2[j] = fma(dy[j], dy[j], d2[j]);
+#pragma unroll
+      for (int j = 0; j < DW; ++j) d2[j] = fma(dz[j], dz[j], d2[j]);
+#pragma unroll
+      for (int j = 0; j < DW; ++j) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[j]) : "d"(d2[j]));
+#pragma unroll
+      for (int j = 0; j < DW; ++j) y2[j] = __dmul_rn(y[j], y[j]);
+#pragma unroll
+      for (int j = 0; j < DW; ++j) {
+        ee[j] = fma(-d2[j], y2[j], 1.0);
+        y[j] = __dmul_rn(y[j], y2[j]);  // y0^3
+      }
+#pragma unroll
+      for (int j = 0; j < DW; ++j) {
+        q[j] = fma(1.875, ee[j], 1.5);
+        mq[j] = __dmul_rn(mq[j], y[j]);  // -m * y0^3
+      }
+#pragma unroll
+      for (int j = 0; j < DW; ++j) ee[j] = __dmul_rn(mq[j], ee[j]);
+#pragma unroll
+      for (int j = 0; j < DW; ++j) {
+        const double magi = fma(ee[j], q[j], mq[j]);
+        mq[j] = use[j] ? magi : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < DW; ++j) {
+        ax = fma(mq[j], dx[j], ax);
+        ay = fma(mq[j], dy[j], ay);
+        az = fma(mq[j], dz[j], az);
+      }
+    }
   }
   __syncwarp();
 }
@@ -380,6 +441,9 @@ int walk(Ctx* c) {
       return s ? atoi(s) : 0;
     }();
     switch (cfg) {
+      case 16: launch_walk<1, 6>(c, begin, end); break;
+      case 110: launch_walk<1, 10>(c, begin, end); break;
+      case 26: launch_walk<2, 6>(c, begin, end); break;
       case 18: launch_walk<1, 8>(c, begin, end); break;
       case 112: launch_walk<1, 12>(c, begin, end); break;
       case 116: launch_walk<1, 16>(c, begin, end); break;
