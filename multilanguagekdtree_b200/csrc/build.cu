@@ -38,7 +38,8 @@ __global__ void build_root(uint32_t* tstart, uint32_t* tlen, uint32_t* tnode, ui
 __global__ void __launch_bounds__(128) level_stats(Pos3c pos, Lists L, int level, uint32_t mp, int layout,
                                                    uint32_t* __restrict__ tstart, uint32_t* __restrict__ tlen,
                                                    uint32_t* __restrict__ tnode, uint32_t* __restrict__ tmid,
-                                                   uint8_t* __restrict__ tsd, WNode* __restrict__ nodes) {
+                                                   uint8_t* __restrict__ tsd, WNode* __restrict__ nodes,
+                                                   const uint32_t* __restrict__ flat) {
   const uint32_t nseg = 1u << level;
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nseg) return;
@@ -47,8 +48,11 @@ __global__ void __launch_bounds__(128) level_stats(Pos3c pos, Lists L, int level
   double mn[3], mx[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    mn[d] = pos.p[d][L.l[d][a]];
-    mx[d] = pos.p[d][L.l[d][a + len - 1]];
+    mn[d] = mx[d] = 0.0;  // a flat dimension has extent 0 everywhere (its list is not maintained)
+    if (!flat[d]) {
+      mn[d] = pos.p[d][L.l[d][a]];
+      mx[d] = pos.p[d][L.l[d][a + len - 1]];
+    }
   }
   int sd = 0;
   double ext = mx[0] - mn[0];
@@ -103,11 +107,12 @@ __global__ void __launch_bounds__(LVL_THREADS) level_count(Lists L, int level, u
                                                            const uint32_t* __restrict__ tlen,
                                                            const uint8_t* __restrict__ tsd,
                                                            const uint8_t* __restrict__ side,
-                                                           uint32_t* __restrict__ cnt) {
+                                                           uint32_t* __restrict__ cnt,
+                                                           const uint32_t* __restrict__ flat) {
   __shared__ uint32_t wsum[LVL_THREADS / 32];
   const uint32_t seg = blockIdx.x / cps, chunk = blockIdx.x % cps, e = blockIdx.y;
   const uint32_t nseg = 1u << level, off = nseg - 1;
-  if (tsd[off + seg] == e) return;  // the split-dimension list is already partitioned
+  if (tsd[off + seg] == e || flat[e]) return;  // the split-dimension list is already partitioned; flat lists are unused
   const uint32_t a = tstart[off + seg], len = tlen[off + seg];
   const uint32_t* lst = L.l[e];
   uint32_t c = 0;
@@ -130,11 +135,11 @@ __global__ void __launch_bounds__(LVL_THREADS) level_count(Lists L, int level, u
 
 // exclusive scan of each (list, segment) row of chunk counts
 __global__ void __launch_bounds__(256) level_scan(int level, uint32_t cps, const uint8_t* __restrict__ tsd,
-                                                  uint32_t* __restrict__ cnt) {
+                                                  uint32_t* __restrict__ cnt, const uint32_t* __restrict__ flat) {
   __shared__ uint32_t wsum[8];
   const uint32_t seg = blockIdx.x, e = blockIdx.y;
   const uint32_t nseg = 1u << level, off = nseg - 1;
-  if (tsd[off + seg] == e) return;
+  if (tsd[off + seg] == e || flat[e]) return;
   uint32_t* row = cnt + ((uint64_t)e * nseg + seg) * cps;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint32_t carry = 0;
@@ -168,10 +173,12 @@ __global__ void __launch_bounds__(LVL_THREADS) level_scatter(Lists Lin, Lists Lo
                                                              const uint32_t* __restrict__ tmid,
                                                              const uint8_t* __restrict__ tsd,
                                                              const uint8_t* __restrict__ side,
-                                                             const uint32_t* __restrict__ cnt) {
+                                                             const uint32_t* __restrict__ cnt,
+                                                             const uint32_t* __restrict__ flat) {
   constexpr int IPT = LVL_CHUNK / LVL_THREADS;  // 8
   __shared__ uint32_t wtot[LVL_THREADS / 32];
   const uint32_t seg = blockIdx.x / cps, chunk = blockIdx.x % cps, e = blockIdx.y;
+  if (flat[e]) return;
   const uint32_t nseg = 1u << level, off = nseg - 1;
   const uint32_t a = tstart[off + seg], len = tlen[off + seg], mid = tmid[off + seg];
   const uint32_t* lin = Lin.l[e];
@@ -250,7 +257,7 @@ build_bottom(Pos3c pos, const double* __restrict__ mass, Lists L, int level, uin
              const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ tlen,
              const uint32_t* __restrict__ tnode, uint32_t* __restrict__ inv, WNode* __restrict__ nodes,
              double4* __restrict__ ms, uint32_t* __restrict__ perm, uint32_t* __restrict__ rank,
-             PosM* __restrict__ posm) {
+             PosM* __restrict__ posm, const uint32_t* __restrict__ flat) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BotSmem& S = *reinterpret_cast<BotSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -277,9 +284,10 @@ build_bottom(Pos3c pos, const double* __restrict__ mass, Lists L, int level, uin
     S.tab[1] = t;
   }
   __syncthreads();
+  const bool flat1 = flat[1] != 0, flat2 = flat[2] != 0;
   for (uint32_t j = tid; j < len0; j += BOT_THREADS) {
-    S.lst[0][1][j] = (uint16_t)inv[L.l[1][a0 + j]];
-    S.lst[0][2][j] = (uint16_t)inv[L.l[2][a0 + j]];
+    if (!flat1) S.lst[0][1][j] = (uint16_t)inv[L.l[1][a0 + j]];
+    if (!flat2) S.lst[0][2][j] = (uint16_t)inv[L.l[2][a0 + j]];
   }
   __syncthreads();
 
@@ -303,8 +311,11 @@ build_bottom(Pos3c pos, const double* __restrict__ mass, Lists L, int level, uin
       double mn[3], mx[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        mn[d] = pos.p[d][S.gid[S.lst[cur][d][t.a]]];
-        mx[d] = pos.p[d][S.gid[S.lst[cur][d][t.a + t.len - 1]]];
+        mn[d] = mx[d] = 0.0;
+        if (d == 0 || !(d == 1 ? flat1 : flat2)) {
+          mn[d] = pos.p[d][S.gid[S.lst[cur][d][t.a]]];
+          mx[d] = pos.p[d][S.gid[S.lst[cur][d][t.a + t.len - 1]]];
+        }
       }
       int sd = 0;
       double ext = mx[0] - mn[0];
@@ -357,6 +368,7 @@ build_bottom(Pos3c pos, const double* __restrict__ mass, Lists L, int level, uin
     __syncthreads();
     // ---- stable partition of each list inside every segment
     for (int d = 0; d < 3; ++d) {
+      if ((d == 1 && flat1) || (d == 2 && flat2)) continue;  // unused list
       uint32_t el[BOT_IPT], bl[BOT_IPT];
       uint32_t wl = 0;
 #pragma unroll
@@ -532,19 +544,19 @@ int build_tree(Ctx* c) {
     Lists Lin = {{c->list[cur], c->list[cur] + n, c->list[cur] + 2ull * n}};
     Lists Lout = {{c->list[cur ^ 1], c->list[cur ^ 1] + n, c->list[cur ^ 1] + 2ull * n}};
     KDNB_LAUNCH(c, level_stats, (nseg + 127) / 128, 128, 0, pos, Lin, lev, c->mp, c->layout, c->tstart, c->tlen,
-                c->tnode, c->tmid, c->tsd, c->nodes);
+                c->tnode, c->tmid, c->tsd, c->nodes, c->flat);
     KDNB_LAUNCH(c, level_flags, nseg * cps, LVL_THREADS, 0, Lin, lev, cps, c->tstart, c->tlen, c->tmid, c->tsd,
                 c->side);
     KDNB_LAUNCH(c, level_count, dim3(nseg * cps, 3), LVL_THREADS, 0, Lin, lev, cps, c->tstart, c->tlen, c->tsd,
-                c->side, c->chunk_cnt);
-    KDNB_LAUNCH(c, level_scan, dim3(nseg, 3), 256, 0, lev, cps, c->tsd, c->chunk_cnt);
+                c->side, c->chunk_cnt, c->flat);
+    KDNB_LAUNCH(c, level_scan, dim3(nseg, 3), 256, 0, lev, cps, c->tsd, c->chunk_cnt, c->flat);
     KDNB_LAUNCH(c, level_scatter, dim3(nseg * cps, 3), LVL_THREADS, 0, Lin, Lout, lev, cps, c->tstart, c->tlen,
-                c->tmid, c->tsd, c->side, c->chunk_cnt);
+                c->tmid, c->tsd, c->side, c->chunk_cnt, c->flat);
     cur ^= 1;
   }
   Lists Lb = {{c->list[cur], c->list[cur] + n, c->list[cur] + 2ull * n}};
   KDNB_LAUNCH(c, build_bottom, 1u << c->l0, BOT_THREADS, sizeof(BotSmem), pos, c->mass, Lb, c->l0, c->mp,
-              c->layout, c->tstart, c->tlen, c->tnode, c->inv, c->nodes, c->ms, c->perm, c->rank, c->posm);
+              c->layout, c->tstart, c->tlen, c->tnode, c->inv, c->nodes, c->ms, c->perm, c->rank, c->posm, c->flat);
   if (c->l0 > 0) KDNB_LAUNCH(c, build_topup, 1, 1024, 0, c->l0, c->tnode, c->nodes, c->ms);
   KDNB_CHECK_LAUNCH(c);
   c->tree_valid = true;

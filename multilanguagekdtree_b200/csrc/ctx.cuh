@@ -43,6 +43,7 @@ struct Ctx {
   uint32_t* list[2] = {nullptr, nullptr};  // [3][n] per-dimension sorted id lists, ping-pong
   uint32_t* hist = nullptr;                // [3][256][ntiles]
   uint32_t* digit_tot = nullptr;           // [3][256]
+  uint32_t* flat = nullptr;                // [3] 1 = all coordinates of that dimension equal (lives behind digit_tot)
   uint8_t* side = nullptr;                 // [n] 0 = goes left, 1 = goes right at the current level
   uint32_t* inv = nullptr;                 // [n] id -> local slot inside a bottom segment
   uint32_t* tstart = nullptr;              // level tables, level l at offset 2^l - 1

@@ -154,7 +154,8 @@ static int plan(Ctx* c, uint64_t n) {
     if (!rc) rc = dev_alloc(c, &c->list[0], 3 * n);
     if (!rc) rc = dev_alloc(c, &c->list[1], 3 * n);
     if (!rc) rc = dev_alloc(c, &c->hist, 3ull * 256 * c->ntiles);
-    if (!rc) rc = dev_alloc(c, &c->digit_tot, 3 * 256);
+    if (!rc) rc = dev_alloc(c, &c->digit_tot, 3 * 256 + 4);
+    if (!rc) c->flat = c->digit_tot + 3 * 256;
     if (!rc) rc = dev_alloc(c, &c->side, n);
     if (!rc) rc = dev_alloc(c, &c->inv, n);
     if (!rc) rc = dev_alloc(c, &c->tstart, table);

@@ -7,6 +7,8 @@
 // (Parallel/RustVersion/src/quickstat.rs:9-34 called from array_kd_tree.rs:561-562): with the three lists
 // sorted once per step, every node's median is the middle entry of its list segment and the bounding box
 // is its two ends.
+#include <algorithm>
+
 #include "ctx.cuh"
 
 namespace kdnb {
@@ -19,9 +21,11 @@ struct Pos3 {
 template <bool FIRST>
 __global__ void __launch_bounds__(SORT_THREADS) sort_upsweep(Pos3 pos, const uint64_t* __restrict__ keys_in,
                                                              uint32_t n, int shift, uint32_t ntiles,
-                                                             uint32_t* __restrict__ hist) {
+                                                             uint32_t* __restrict__ hist,
+                                                             const uint32_t* __restrict__ flat) {
   __shared__ uint32_t h[256];
   const int d = blockIdx.y;
+  if (flat[d]) return;  // all coordinates of this dimension are equal: its list is never consulted (build.cu)
   const uint32_t tile = blockIdx.x;
   h[threadIdx.x] = 0;
   __syncthreads();
@@ -40,8 +44,10 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_upsweep(Pos3 pos, const uin
 
 // ---- pass kernel 2: exclusive scan of every (dimension, digit) row over tiles; row totals to tot[]
 __global__ void __launch_bounds__(256) sort_scan_rows(uint32_t* __restrict__ hist, uint32_t ntiles,
-                                                      uint32_t* __restrict__ tot) {
+                                                      uint32_t* __restrict__ tot,
+                                                      const uint32_t* __restrict__ flat) {
   __shared__ uint32_t wsum[8];
+  if (flat[blockIdx.y]) return;
   uint32_t* row = hist + ((uint64_t)blockIdx.y * 256 + blockIdx.x) * ntiles;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint32_t carry = 0;
@@ -78,11 +84,13 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const u
                                                                uint32_t* __restrict__ vals_out, uint32_t n,
                                                                int shift, uint32_t ntiles,
                                                                const uint32_t* __restrict__ hist,
-                                                               const uint32_t* __restrict__ tot) {
+                                                               const uint32_t* __restrict__ tot,
+                                                               const uint32_t* __restrict__ flat) {
   __shared__ uint32_t wcnt[SORT_THREADS / 32][256];
   __shared__ uint32_t base[256];
   __shared__ uint32_t wsum[8];
   const int d = blockIdx.y;
+  if (flat[d]) return;
   const uint32_t tile = blockIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
@@ -151,30 +159,48 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const u
   }
 }
 
+// flat[d] = 1 when every particle has the same coordinate d (planar inputs: the reference's ring has z == 0 for
+// ever).  Such a dimension has extent 0 in every node, so it is never the split dimension (array_kd_tree.rs:551-556
+// keeps the lower dimension on ties) and its sorted list is never consulted: sorting and partitioning it is skipped.
+// Dimension 0 is always kept — it is the tie winner when all extents are 0 and it orders the leaves.
+__global__ void flat_init(uint32_t* flat) {
+  if (threadIdx.x < 3) flat[threadIdx.x] = threadIdx.x > 0 ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) flat_detect(Pos3 pos, uint32_t n, uint32_t* __restrict__ flat) {
+  const int d = blockIdx.y + 1;
+  const uint64_t k0 = f64_key(pos.p[d][0]);
+  bool differs = false;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    differs |= f64_key(pos.p[d][i]) != k0;
+  if (differs) flat[d] = 0u;
+}
+
 // Sorted lists end in c->list[0] (8 passes: positions -> buf1 -> buf0 -> ... -> buf0).
 int sort_lists(Ctx* c) {
   const uint32_t n = (uint32_t)c->n;
   const uint32_t nt = c->ntiles;
   Pos3 pos = {{c->pos[0], c->pos[1], c->pos[2]}};
   dim3 gt(nt, 3), gs(256, 3);
+  KDNB_LAUNCH(c, flat_init, 1, 32, 0, c->flat);
+  KDNB_LAUNCH(c, flat_detect, dim3(std::min<uint32_t>((n + 255) / 256, 1184u), 2), 256, 0, pos, n, c->flat);
   for (int pass = 0; pass < 8; ++pass) {
     const int shift = 8 * pass;
     const int src = (pass & 1) ? 1 : 0, dst = src ^ 1;  // pass 0 reads positions, writes buf1
     if (pass == 0) {
-      KDNB_LAUNCH(c, sort_upsweep<true>, gt, SORT_THREADS, 0, pos, nullptr, n, shift, nt, c->hist);
+      KDNB_LAUNCH(c, sort_upsweep<true>, gt, SORT_THREADS, 0, pos, nullptr, n, shift, nt, c->hist, c->flat);
     } else {
-      KDNB_LAUNCH(c, sort_upsweep<false>, gt, SORT_THREADS, 0, pos, c->keys[src], n, shift, nt, c->hist);
+      KDNB_LAUNCH(c, sort_upsweep<false>, gt, SORT_THREADS, 0, pos, c->keys[src], n, shift, nt, c->hist, c->flat);
     }
-    KDNB_LAUNCH(c, sort_scan_rows, gs, 256, 0, c->hist, nt, c->digit_tot);
+    KDNB_LAUNCH(c, sort_scan_rows, gs, 256, 0, c->hist, nt, c->digit_tot, c->flat);
     if (pass == 0) {
       KDNB_LAUNCH(c, (sort_downsweep<true, false>), gt, SORT_THREADS, 0, pos, nullptr, nullptr, c->keys[1],
-                  c->list[1], n, shift, nt, c->hist, c->digit_tot);
+                  c->list[1], n, shift, nt, c->hist, c->digit_tot, c->flat);
     } else if (pass == 7) {
       KDNB_LAUNCH(c, (sort_downsweep<false, true>), gt, SORT_THREADS, 0, pos, c->keys[src], c->list[src],
-                  c->keys[dst], c->list[dst], n, shift, nt, c->hist, c->digit_tot);
+                  c->keys[dst], c->list[dst], n, shift, nt, c->hist, c->digit_tot, c->flat);
     } else {
       KDNB_LAUNCH(c, (sort_downsweep<false, false>), gt, SORT_THREADS, 0, pos, c->keys[src], c->list[src],
-                  c->keys[dst], c->list[dst], n, shift, nt, c->hist, c->digit_tot);
+                  c->keys[dst], c->list[dst], n, shift, nt, c->hist, c->digit_tot, c->flat);
     }
   }
   KDNB_CHECK_LAUNCH(c);
