@@ -253,7 +253,7 @@ struct BotSmem {
 };
 
 __global__ void __launch_bounds__(BOT_THREADS)
-build_bottom(Pos3c pos, const double* __restrict__ mass, Lists L, int level, uint32_t mp, int layout,
+build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_t mp, int layout,
              const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ tlen,
              const uint32_t* __restrict__ tnode, uint32_t* __restrict__ inv, WNode* __restrict__ nodes,
              double4* __restrict__ ms, uint32_t* __restrict__ perm, uint32_t* __restrict__ rank,
@@ -421,38 +421,51 @@ build_bottom(Pos3c pos, const double* __restrict__ mass, Lists L, int level, uin
     cur ^= 1;
   }
 
-  // ---- leaves: ascending id order (canonical), sequential m / sum(m*p) (array_kd_tree.rs:534-539 order of ops)
+  // ---- leaves.  (1) one thread per leaf puts its slots in ascending particle-id order (canonical leaf order);
+  //      (2) one thread per SLOT gathers {x,y,z,m} (one sector of the AoS copy, all gathers of the CTA in flight
+  //          together) and writes perm / rank / posm coalesced;
+  //      (3) one thread per leaf sums m and m*p sequentially in that order (array_kd_tree.rs:534-539 order of ops).
   const uint32_t hend = 2u << depth;
+  uint16_t* order = S.lst[cur ^ 1][0];  // free buffer: tree slot (local) -> local id
   for (uint32_t h = 1 + tid; h < hend; h += BOT_THREADS) {
     BotTab t = S.tab[h];
     if (t.kind != 1) continue;
     uint32_t g[32];
+    uint16_t ls[32];
     for (uint32_t k = 0; k < t.len; ++k) {
-      uint32_t v = S.gid[S.lst[cur][0][t.a + k]];
+      const uint16_t l = S.lst[cur][0][t.a + k];
+      const uint32_t v = S.gid[l];
       int j = (int)k - 1;
       while (j >= 0 && g[j] > v) {
         g[j + 1] = g[j];
+        ls[j + 1] = ls[j];
         --j;
       }
       g[j + 1] = v;
+      ls[j + 1] = l;
     }
+    for (uint32_t k = 0; k < t.len; ++k) order[t.a + k] = ls[k];
+  }
+  __syncthreads();
+  for (uint32_t p = tid; p < len0; p += BOT_THREADS) {
+    const uint32_t id = S.gid[order[p]];
+    const PosM q = pm[id];
+    perm[a0 + p] = id;
+    rank[id] = a0 + p;
+    posm[a0 + p] = q;
+  }
+  __syncthreads();
+  for (uint32_t h = 1 + tid; h < hend; h += BOT_THREADS) {
+    BotTab t = S.tab[h];
+    if (t.kind != 1) continue;
     double m = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
     const uint32_t first = a0 + t.a;
     for (uint32_t k = 0; k < t.len; ++k) {
-      const uint32_t id = g[k];
-      const double mm = mass[id], x = pos.p[0][id], y = pos.p[1][id], z = pos.p[2][id];
-      m = __dadd_rn(m, mm);
-      sx = __dadd_rn(sx, __dmul_rn(mm, x));
-      sy = __dadd_rn(sy, __dmul_rn(mm, y));
-      sz = __dadd_rn(sz, __dmul_rn(mm, z));
-      perm[first + k] = id;
-      rank[id] = first + k;
-      PosM pm;
-      pm.x = x;
-      pm.y = y;
-      pm.z = z;
-      pm.m = mm;
-      posm[first + k] = pm;
+      const PosM q = posm[first + k];  // written by this CTA just above
+      m = __dadd_rn(m, q.m);
+      sx = __dadd_rn(sx, __dmul_rn(q.m, q.x));
+      sy = __dadd_rn(sy, __dmul_rn(q.m, q.y));
+      sz = __dadd_rn(sz, __dmul_rn(q.m, q.z));
     }
     ms[t.node] = make_double4(m, sx, sy, sz);
     WNode* nd = &nodes[t.node];
@@ -555,7 +568,7 @@ int build_tree(Ctx* c) {
     cur ^= 1;
   }
   Lists Lb = {{c->list[cur], c->list[cur] + n, c->list[cur] + 2ull * n}};
-  KDNB_LAUNCH(c, build_bottom, 1u << c->l0, BOT_THREADS, sizeof(BotSmem), pos, c->mass, Lb, c->l0, c->mp,
+  KDNB_LAUNCH(c, build_bottom, 1u << c->l0, BOT_THREADS, sizeof(BotSmem), pos, c->pm, Lb, c->l0, c->mp,
               c->layout, c->tstart, c->tlen, c->tnode, c->inv, c->nodes, c->ms, c->perm, c->rank, c->posm, c->flat);
   if (c->l0 > 0) KDNB_LAUNCH(c, build_topup, 1, 1024, 0, c->l0, c->tnode, c->nodes, c->ms);
   KDNB_CHECK_LAUNCH(c);

@@ -37,6 +37,7 @@ struct Ctx {
   double* mass = nullptr;
   double* radius = nullptr;
   kdnb_particle* aos = nullptr;  // staging for AoS <-> SoA conversion
+  PosM* pm = nullptr;            // {x, y, z, m} in original order: one-sector gathers for the bottom build kernel
 
   // build scratch
   uint64_t* keys[2] = {nullptr, nullptr};  // [3][n] radix keys, ping-pong
@@ -45,12 +46,12 @@ struct Ctx {
   uint32_t* digit_tot = nullptr;           // [3][256]
   uint32_t* flat = nullptr;                // [3] 1 = all coordinates of that dimension equal (lives behind digit_tot)
   uint8_t* side = nullptr;                 // [n] 0 = goes left, 1 = goes right at the current level
-  uint32_t* inv = nullptr;                 // [n] id -> local slot inside a bottom segment
   uint32_t* tstart = nullptr;              // level tables, level l at offset 2^l - 1
   uint32_t* tlen = nullptr;
   uint32_t* tnode = nullptr;
   uint32_t* tmid = nullptr;
   uint8_t* tsd = nullptr;
+  uint32_t* inv = nullptr;                 // [n] id -> local slot inside a bottom segment
   uint32_t* chunk_cnt = nullptr;           // [3][nseg][chunks] left counts per chunk
   uint64_t table_cap = 0, chunk_cap = 0;
 

@@ -100,6 +100,7 @@ static void free_all(Ctx* c) {
   fr(c->hist);
   fr(c->digit_tot);
   fr(c->side);
+  fr(c->pm);
   fr(c->inv);
   fr(c->tstart);
   fr(c->tlen);
@@ -157,6 +158,7 @@ static int plan(Ctx* c, uint64_t n) {
     if (!rc) rc = dev_alloc(c, &c->digit_tot, 3 * 256 + 4);
     if (!rc) c->flat = c->digit_tot + 3 * 256;
     if (!rc) rc = dev_alloc(c, &c->side, n);
+    if (!rc) rc = dev_alloc(c, &c->pm, n);
     if (!rc) rc = dev_alloc(c, &c->inv, n);
     if (!rc) rc = dev_alloc(c, &c->tstart, table);
     if (!rc) rc = dev_alloc(c, &c->tlen, table);

@@ -13,7 +13,7 @@ struct V3 {
 // thread i = particle i (original order); its acceleration lives at tree slot rank[i]
 __global__ void __launch_bounds__(256) kick_drift_kernel(uint32_t n, double dt, V3 pos, V3 vel,
                                                          const uint32_t* __restrict__ rank,
-                                                         const double* __restrict__ acc_t) {
+                                                         const double* __restrict__ acc_t, PosM* __restrict__ pm) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t j = rank[i];
@@ -24,15 +24,21 @@ __global__ void __launch_bounds__(256) kick_drift_kernel(uint32_t n, double dt, 
   vel.p[0][i] = v0;
   vel.p[1][i] = v1;
   vel.p[2][i] = v2;
-  pos.p[0][i] = __dadd_rn(pos.p[0][i], __dmul_rn(dt, v0));      // dx = dt*v; p += dx     (:653-658)
-  pos.p[1][i] = __dadd_rn(pos.p[1][i], __dmul_rn(dt, v1));
-  pos.p[2][i] = __dadd_rn(pos.p[2][i], __dmul_rn(dt, v2));
+  const double x = __dadd_rn(pos.p[0][i], __dmul_rn(dt, v0));  // dx = dt*v; p += dx     (:653-658)
+  const double y = __dadd_rn(pos.p[1][i], __dmul_rn(dt, v1));
+  const double z = __dadd_rn(pos.p[2][i], __dmul_rn(dt, v2));
+  pos.p[0][i] = x;
+  pos.p[1][i] = y;
+  pos.p[2][i] = z;
+  pm[i].x = x;  // AoS mirror read by the next build
+  pm[i].y = y;
+  pm[i].z = z;
 }
 
 int kick_drift(Ctx* c, double dt) {
   const uint32_t n = (uint32_t)c->n;
   V3 pos = {{c->pos[0], c->pos[1], c->pos[2]}}, vel = {{c->vel[0], c->vel[1], c->vel[2]}};
-  KDNB_LAUNCH(c, kick_drift_kernel, (n + 255) / 256, 256, 0, n, dt, pos, vel, c->rank, c->acc_t);
+  KDNB_LAUNCH(c, kick_drift_kernel, (n + 255) / 256, 256, 0, n, dt, pos, vel, c->rank, c->acc_t, c->pm);
   KDNB_CHECK_LAUNCH(c);
   // a[k] = 0 (:659-661)
   KDNB_CUDA_TRY(c, cudaMemsetAsync(c->acc_t, 0, 3ull * c->n * sizeof(double), c->stream));
@@ -42,7 +48,7 @@ int kick_drift(Ctx* c, double dt) {
 
 __global__ void __launch_bounds__(256) aos_to_soa_kernel(uint32_t n, const kdnb_particle* __restrict__ aos, V3 pos,
                                                          V3 vel, double* __restrict__ radius,
-                                                         double* __restrict__ mass) {
+                                                         double* __restrict__ mass, PosM* __restrict__ pm) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double2* q = reinterpret_cast<const double2*>(aos + i);
@@ -55,6 +61,12 @@ __global__ void __launch_bounds__(256) aos_to_soa_kernel(uint32_t n, const kdnb_
   vel.p[2][i] = c2.y;
   radius[i] = d.x;
   mass[i] = d.y;
+  PosM rec;
+  rec.x = a.x;
+  rec.y = a.y;
+  rec.z = b.x;
+  rec.m = d.y;
+  pm[i] = rec;
 }
 
 __global__ void __launch_bounds__(256) soa_to_aos_kernel(uint32_t n, kdnb_particle* __restrict__ aos, V3 pos, V3 vel,
@@ -72,7 +84,7 @@ __global__ void __launch_bounds__(256) soa_to_aos_kernel(uint32_t n, kdnb_partic
 int aos_to_soa(Ctx* c) {
   const uint32_t n = (uint32_t)c->n;
   V3 pos = {{c->pos[0], c->pos[1], c->pos[2]}}, vel = {{c->vel[0], c->vel[1], c->vel[2]}};
-  KDNB_LAUNCH(c, aos_to_soa_kernel, (n + 255) / 256, 256, 0, n, c->aos, pos, vel, c->radius, c->mass);
+  KDNB_LAUNCH(c, aos_to_soa_kernel, (n + 255) / 256, 256, 0, n, c->aos, pos, vel, c->radius, c->mass, c->pm);
   KDNB_CHECK_LAUNCH(c);
   return 0;
 }
