@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(128) level_stats(Pos3c pos, Lists L, int level
                                                    uint32_t* __restrict__ tstart, uint32_t* __restrict__ tlen,
                                                    uint32_t* __restrict__ tnode, uint32_t* __restrict__ tmid,
                                                    uint8_t* __restrict__ tsd, WNode* __restrict__ nodes,
-                                                   const uint32_t* __restrict__ flat) {
+                                                   const uint32_t* __restrict__ flat, const uint32_t* __restrict__ rk,
+                                                   uint32_t n, uint32_t* __restrict__ tmr) {
   const uint32_t nseg = 1u << level;
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nseg) return;
@@ -65,7 +66,8 @@ __global__ void __launch_bounds__(128) level_stats(Pos3c pos, Lists L, int level
     }
   }
   const uint32_t half = len / 2, mid = a + half;
-  const double split_val = pos.p[sd][L.l[sd][mid]];
+  const uint32_t mid_id = L.l[sd][mid];
+  const double split_val = pos.p[sd][mid_id];
   const uint32_t nleft = (uint32_t)subtree_nodes(half, mp, layout);
   WNode* nd = &nodes[node];
   nd->size2 = __dmul_rn(ext, ext);
@@ -75,6 +77,7 @@ __global__ void __launch_bounds__(128) level_stats(Pos3c pos, Lists L, int level
   nd->b = WN_INTERNAL | (uint32_t)sd;
   tsd[off + s] = (uint8_t)sd;
   tmid[off + s] = mid;
+  tmr[off + s] = rk[(uint64_t)sd * n + mid_id];
   const uint32_t coff = 2 * nseg - 1;
   tstart[coff + 2 * s] = a;
   tlen[coff + 2 * s] = half;
@@ -84,42 +87,29 @@ __global__ void __launch_bounds__(128) level_stats(Pos3c pos, Lists L, int level
   tnode[coff + 2 * s + 1] = node + 1 + nleft;
 }
 
-// side[id] = 0 if the particle falls in the left half of its node's split-dimension list, else 1
-__global__ void __launch_bounds__(LVL_THREADS) level_flags(Lists L, int level, uint32_t cps,
-                                                           const uint32_t* __restrict__ tstart,
-                                                           const uint32_t* __restrict__ tlen,
-                                                           const uint32_t* __restrict__ tmid,
-                                                           const uint8_t* __restrict__ tsd,
-                                                           uint8_t* __restrict__ side) {
-  const uint32_t seg = blockIdx.x / cps, chunk = blockIdx.x % cps;
-  const uint32_t off = (1u << level) - 1;
-  const uint32_t a = tstart[off + seg], len = tlen[off + seg], mid = tmid[off + seg];
-  const uint32_t* lst = L.l[tsd[off + seg]];
-#pragma unroll
-  for (int k = 0; k < LVL_CHUNK / LVL_THREADS; ++k) {
-    uint32_t o = chunk * LVL_CHUNK + k * LVL_THREADS + threadIdx.x;
-    if (o < len) side[lst[a + o]] = (a + o >= mid) ? 1 : 0;
-  }
-}
-
+// "goes left" is decided without any per-level flag pass: rk[d][id] is the rank of particle id in the INITIAL sorted
+// list of dimension d (sort.cu).  Stable partitions keep every segment of list d ordered by rk[d], so the left half of
+// a node split along sd is exactly { id : rk[sd][id] < rk[sd][id of the element at mid] } (tmr[] holds that rank).
 __global__ void __launch_bounds__(LVL_THREADS) level_count(Lists L, int level, uint32_t cps,
                                                            const uint32_t* __restrict__ tstart,
                                                            const uint32_t* __restrict__ tlen,
                                                            const uint8_t* __restrict__ tsd,
-                                                           const uint8_t* __restrict__ side,
+                                                           const uint32_t* __restrict__ rk, uint32_t n,
+                                                           const uint32_t* __restrict__ tmr,
                                                            uint32_t* __restrict__ cnt,
                                                            const uint32_t* __restrict__ flat) {
   __shared__ uint32_t wsum[LVL_THREADS / 32];
   const uint32_t seg = blockIdx.x / cps, chunk = blockIdx.x % cps, e = blockIdx.y;
   const uint32_t nseg = 1u << level, off = nseg - 1;
   if (tsd[off + seg] == e || flat[e]) return;  // the split-dimension list is already partitioned; flat lists are unused
-  const uint32_t a = tstart[off + seg], len = tlen[off + seg];
+  const uint32_t a = tstart[off + seg], len = tlen[off + seg], rmid = tmr[off + seg];
   const uint32_t* lst = L.l[e];
+  const uint32_t* rks = rk + (uint64_t)tsd[off + seg] * n;
   uint32_t c = 0;
 #pragma unroll
   for (int k = 0; k < LVL_CHUNK / LVL_THREADS; ++k) {
     uint32_t o = chunk * LVL_CHUNK + k * LVL_THREADS + threadIdx.x;
-    if (o < len) c += (side[lst[a + o]] == 0);
+    if (o < len) c += (rks[lst[a + o]] < rmid);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
@@ -172,7 +162,8 @@ __global__ void __launch_bounds__(LVL_THREADS) level_scatter(Lists Lin, Lists Lo
                                                              const uint32_t* __restrict__ tlen,
                                                              const uint32_t* __restrict__ tmid,
                                                              const uint8_t* __restrict__ tsd,
-                                                             const uint8_t* __restrict__ side,
+                                                             const uint32_t* __restrict__ rk, uint32_t n,
+                                                             const uint32_t* __restrict__ tmr,
                                                              const uint32_t* __restrict__ cnt,
                                                              const uint32_t* __restrict__ flat) {
   constexpr int IPT = LVL_CHUNK / LVL_THREADS;  // 8
@@ -195,6 +186,8 @@ __global__ void __launch_bounds__(LVL_THREADS) level_scatter(Lists Lin, Lists Lo
     }
     return;
   }
+  const uint32_t* rks = rk + (uint64_t)tsd[off + seg] * n;
+  const uint32_t rmid = tmr[off + seg];
   uint32_t id[IPT], bl[IPT];
   uint32_t wl = 0;
 #pragma unroll
@@ -202,7 +195,7 @@ __global__ void __launch_bounds__(LVL_THREADS) level_scatter(Lists Lin, Lists Lo
     uint32_t o = wbase_off + k * 32 + lane;
     bool valid = o < len;
     id[k] = valid ? lin[a + o] : 0u;
-    bool isleft = valid && (side[id[k]] == 0);
+    bool isleft = valid && (rks[id[k]] < rmid);
     bl[k] = __ballot_sync(0xffffffffu, isleft);
     wl += __popc(bl[k]);
   }
@@ -557,14 +550,12 @@ int build_tree(Ctx* c) {
     Lists Lin = {{c->list[cur], c->list[cur] + n, c->list[cur] + 2ull * n}};
     Lists Lout = {{c->list[cur ^ 1], c->list[cur ^ 1] + n, c->list[cur ^ 1] + 2ull * n}};
     KDNB_LAUNCH(c, level_stats, (nseg + 127) / 128, 128, 0, pos, Lin, lev, c->mp, c->layout, c->tstart, c->tlen,
-                c->tnode, c->tmid, c->tsd, c->nodes, c->flat);
-    KDNB_LAUNCH(c, level_flags, nseg * cps, LVL_THREADS, 0, Lin, lev, cps, c->tstart, c->tlen, c->tmid, c->tsd,
-                c->side);
+                c->tnode, c->tmid, c->tsd, c->nodes, c->flat, c->rk, n, c->tmr);
     KDNB_LAUNCH(c, level_count, dim3(nseg * cps, 3), LVL_THREADS, 0, Lin, lev, cps, c->tstart, c->tlen, c->tsd,
-                c->side, c->chunk_cnt, c->flat);
+                c->rk, n, c->tmr, c->chunk_cnt, c->flat);
     KDNB_LAUNCH(c, level_scan, dim3(nseg, 3), 256, 0, lev, cps, c->tsd, c->chunk_cnt, c->flat);
     KDNB_LAUNCH(c, level_scatter, dim3(nseg * cps, 3), LVL_THREADS, 0, Lin, Lout, lev, cps, c->tstart, c->tlen,
-                c->tmid, c->tsd, c->side, c->chunk_cnt, c->flat);
+                c->tmid, c->tsd, c->rk, n, c->tmr, c->chunk_cnt, c->flat);
     cur ^= 1;
   }
   Lists Lb = {{c->list[cur], c->list[cur] + n, c->list[cur] + 2ull * n}};

@@ -45,7 +45,8 @@ struct Ctx {
   uint32_t* hist = nullptr;                // [3][256][ntiles]
   uint32_t* digit_tot = nullptr;           // [3][256]
   uint32_t* flat = nullptr;                // [3] 1 = all coordinates of that dimension equal (lives behind digit_tot)
-  uint8_t* side = nullptr;                 // [n] 0 = goes left, 1 = goes right at the current level
+  uint32_t* rk = nullptr;                  // [3][n] rank of every particle in the initial sorted list of each dimension
+  uint32_t* tmr = nullptr;                 // level table: rk of the median element of every segment
   uint32_t* tstart = nullptr;              // level tables, level l at offset 2^l - 1
   uint32_t* tlen = nullptr;
   uint32_t* tnode = nullptr;

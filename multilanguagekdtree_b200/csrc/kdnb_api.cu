@@ -99,7 +99,8 @@ static void free_all(Ctx* c) {
   fr(c->list[1]);
   fr(c->hist);
   fr(c->digit_tot);
-  fr(c->side);
+  fr(c->rk);
+  fr(c->tmr);
   fr(c->pm);
   fr(c->inv);
   fr(c->tstart);
@@ -157,7 +158,8 @@ static int plan(Ctx* c, uint64_t n) {
     if (!rc) rc = dev_alloc(c, &c->hist, 3ull * 256 * c->ntiles);
     if (!rc) rc = dev_alloc(c, &c->digit_tot, 3 * 256 + 4);
     if (!rc) c->flat = c->digit_tot + 3 * 256;
-    if (!rc) rc = dev_alloc(c, &c->side, n);
+    if (!rc) rc = dev_alloc(c, &c->rk, 3 * n);
+    if (!rc) rc = dev_alloc(c, &c->tmr, table);
     if (!rc) rc = dev_alloc(c, &c->pm, n);
     if (!rc) rc = dev_alloc(c, &c->inv, n);
     if (!rc) rc = dev_alloc(c, &c->tstart, table);

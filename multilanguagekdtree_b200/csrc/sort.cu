@@ -175,6 +175,15 @@ __global__ void __launch_bounds__(256) flat_detect(Pos3 pos, uint32_t n, uint32_
   if (differs) flat[d] = 0u;
 }
 
+// rk[d][id] = rank of particle id in the sorted list of dimension d (read by the global partition levels, build.cu)
+__global__ void __launch_bounds__(256) rank_from_lists(const uint32_t* __restrict__ lists, uint32_t n,
+                                                       uint32_t* __restrict__ rk, const uint32_t* __restrict__ flat) {
+  const int d = blockIdx.y;
+  if (flat[d]) return;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rk[(uint64_t)d * n + lists[(uint64_t)d * n + i]] = i;
+}
+
 // Sorted lists end in c->list[0] (8 passes: positions -> buf1 -> buf0 -> ... -> buf0).
 int sort_lists(Ctx* c) {
   const uint32_t n = (uint32_t)c->n;
@@ -203,6 +212,7 @@ int sort_lists(Ctx* c) {
                   c->keys[dst], c->list[dst], n, shift, nt, c->hist, c->digit_tot, c->flat);
     }
   }
+  if (c->l0 > 0) KDNB_LAUNCH(c, rank_from_lists, dim3((n + 255) / 256, 3), 256, 0, c->list[0], n, c->rk, c->flat);
   KDNB_CHECK_LAUNCH(c);
   return 0;
 }

@@ -107,6 +107,7 @@ __device__ __forceinline__ void drain_list(const Rec32* __restrict__ lpos, const
     // the FP64 pipe idled on its own latency: profiles/README.md).  The list is padded to a multiple of DW with
     // masked-out entries.
     constexpr int DW = 4;
+    const uint32_t lanebit = 1u << lane;
     const int padded = (cnt + DW - 1) / DW * DW;
     if (lane < padded - cnt) {
       Rec32 z;
@@ -117,11 +118,15 @@ __device__ __forceinline__ void drain_list(const Rec32* __restrict__ lpos, const
     __syncwarp();
     for (int i = 0; i < padded; i += DW) {
       double dx[DW], dy[DW], dz[DW], d2[DW], y[DW], y2[DW], ee[DW], mq[DW], q[DW];
-      bool use[DW];
+      uint32_t use[DW];
+      {  // the DW masks in two 16-byte loads ({mask, flag} pairs)
+        const uint4 m01 = *reinterpret_cast<const uint4*>(&lmask[i]);
+        const uint4 m23 = *reinterpret_cast<const uint4*>(&lmask[i + 2]);
+        use[0] = m01.x & lanebit, use[1] = m01.z & lanebit, use[2] = m23.x & lanebit, use[3] = m23.z & lanebit;
+      }
 #pragma unroll
       for (int j = 0; j < DW; ++j) {
         const Rec32 e = lpos[i + j];
-        use[j] = (lmask[i + j].x >> lane) & 1u;
         dx[j] = __dsub_rn(px, e.a);
         dy[j] = __dsub_rn(py, e.b);
         dz[j] = __dsub_rn(pz, e.c);
@@ -152,7 +157,7 @@ __device__ __forceinline__ void drain_list(const Rec32* __restrict__ lpos, const
 #pragma unroll
       for (int j = 0; j < DW; ++j) {
         const double magi = fma(ee[j], q[j], mq[j]);
-        mq[j] = use[j] ? magi : 0.0;
+        mq[j] = use[j] ? magi : 0.0;  // (ptxas turns predicated DFMAs into DFMA + 2 FSEL each: select once here)
       }
 #pragma unroll
       for (int j = 0; j < DW; ++j) {
