@@ -88,7 +88,10 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const u
                                                                const uint32_t* __restrict__ flat) {
   __shared__ uint32_t wcnt[SORT_THREADS / 32][256];
   __shared__ uint32_t base[256];
+  __shared__ uint32_t toff[256];
   __shared__ uint32_t wsum[8];
+  __shared__ uint64_t skey[SORT_TILE];
+  __shared__ uint32_t sval[SORT_TILE];
   const int d = blockIdx.y;
   if (flat[d]) return;
   const uint32_t tile = blockIdx.x;
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const u
     __syncwarp();
   }
   __syncthreads();
-  {  // exclusive scan over warps, per digit
+  {  // exclusive scan over warps, per digit; then exclusive scan over digits = start of each digit's run in the tile
     uint32_t run = 0;
 #pragma unroll
     for (int k = 0; k < SORT_THREADS / 32; ++k) {
@@ -145,16 +148,45 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const u
       wcnt[k][threadIdx.x] = run;
       run += t;
     }
+    uint32_t x = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    uint32_t wp = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < w) wp += wsum[k];
+    toff[threadIdx.x] = wp + x - run;
   }
   __syncthreads();
+  // stage the tile in digit order in shared memory, then write it out in runs: consecutive threads write consecutive
+  // addresses inside each digit's run (the direct scatter wrote 12-byte granules all over the output)
 #pragma unroll
   for (int r = 0; r < SORT_IPT; ++r) {
     uint64_t i = start + r * 32 + lane;
     if (i < n) {
       uint32_t dg = (uint32_t)((key[r] >> shift) & 255u);
-      uint64_t dst = (uint64_t)d * n + base[dg] + wcnt[w][dg] + rk[r];
-      if (!LAST) keys_out[dst] = key[r];
-      vals_out[dst] = val[r];
+      uint32_t p = toff[dg] + wcnt[w][dg] + rk[r];
+      skey[p] = key[r];
+      sval[p] = val[r];
+    }
+  }
+  __syncthreads();
+  const uint64_t tile_base = (uint64_t)tile * SORT_TILE;
+  const uint32_t nvalid = (uint32_t)min((uint64_t)SORT_TILE, (uint64_t)n - tile_base);
+#pragma unroll
+  for (int k = 0; k < SORT_IPT; ++k) {
+    const uint32_t p = k * SORT_THREADS + threadIdx.x;
+    if (p < nvalid) {
+      const uint64_t kk = skey[p];
+      const uint32_t dg = (uint32_t)((kk >> shift) & 255u);
+      const uint64_t dst = (uint64_t)d * n + base[dg] + (p - toff[dg]);
+      if (!LAST) keys_out[dst] = kk;
+      vals_out[dst] = sval[p];
     }
   }
 }
