@@ -123,39 +123,6 @@ __global__ void __launch_bounds__(LVL_THREADS) level_count(Lists L, int level, u
   }
 }
 
-// exclusive scan of each (list, segment) row of chunk counts
-__global__ void __launch_bounds__(256) level_scan(int level, uint32_t cps, const uint8_t* __restrict__ tsd,
-                                                  uint32_t* __restrict__ cnt, const uint32_t* __restrict__ flat) {
-  __shared__ uint32_t wsum[8];
-  const uint32_t seg = blockIdx.x, e = blockIdx.y;
-  const uint32_t nseg = 1u << level, off = nseg - 1;
-  if (tsd[off + seg] == e || flat[e]) return;
-  uint32_t* row = cnt + ((uint64_t)e * nseg + seg) * cps;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint32_t carry = 0;
-  for (uint32_t base = 0; base < cps; base += 256) {
-    uint32_t i = base + threadIdx.x;
-    uint32_t v = i < cps ? row[i] : 0u, x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) wsum[w] = x;
-    __syncthreads();
-    uint32_t wp = 0, total = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      uint32_t t = wsum[k];
-      if (k < w) wp += t;
-      total += t;
-    }
-    if (i < cps) row[i] = carry + wp + x - v;
-    carry += total;
-    __syncthreads();
-  }
-}
-
 // stable partition of list e inside each segment (copy for the split-dimension list)
 __global__ void __launch_bounds__(LVL_THREADS) level_scatter(Lists Lin, Lists Lout, int level, uint32_t cps,
                                                              const uint32_t* __restrict__ tstart,
@@ -205,7 +172,21 @@ __global__ void __launch_bounds__(LVL_THREADS) level_scatter(Lists Lin, Lists Lo
 #pragma unroll
   for (int k = 0; k < LVL_THREADS / 32; ++k)
     if (k < w) wbase += wtot[k];
-  const uint32_t leftbase = cnt[((uint64_t)e * nseg + seg) * cps + chunk];  // lefts in earlier chunks of the segment
+  // lefts in the earlier chunks of this segment: block-wide sum of their counts (replaces a separate scan kernel)
+  __shared__ uint32_t lbsum[LVL_THREADS / 32];
+  uint32_t lb = 0;
+  {
+    const uint32_t* row = cnt + ((uint64_t)e * nseg + seg) * cps;
+    for (uint32_t k = threadIdx.x; k < chunk; k += LVL_THREADS) lb += row[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lb += __shfl_xor_sync(0xffffffffu, lb, o);
+    if (lane == 0) lbsum[w] = lb;
+    __syncthreads();
+    lb = 0;
+#pragma unroll
+    for (int k = 0; k < LVL_THREADS / 32; ++k) lb += lbsum[k];
+  }
+  const uint32_t leftbase = lb;
   uint32_t pre = wbase;
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
@@ -553,7 +534,6 @@ int build_tree(Ctx* c) {
                 c->tnode, c->tmid, c->tsd, c->nodes, c->flat, c->rk, n, c->tmr);
     KDNB_LAUNCH(c, level_count, dim3(nseg * cps, 3), LVL_THREADS, 0, Lin, lev, cps, c->tstart, c->tlen, c->tsd,
                 c->rk, n, c->tmr, c->chunk_cnt, c->flat);
-    KDNB_LAUNCH(c, level_scan, dim3(nseg, 3), 256, 0, lev, cps, c->tsd, c->chunk_cnt, c->flat);
     KDNB_LAUNCH(c, level_scatter, dim3(nseg * cps, 3), LVL_THREADS, 0, Lin, Lout, lev, cps, c->tstart, c->tlen,
                 c->tmid, c->tsd, c->rk, n, c->tmr, c->chunk_cnt, c->flat);
     cur ^= 1;

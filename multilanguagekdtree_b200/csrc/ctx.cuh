@@ -9,7 +9,7 @@ namespace kdnb {
 
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_IPT = 8;
-constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 2048 keys per CTA
+constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // keys per CTA
 constexpr int LVL_THREADS = 256;
 constexpr int LVL_CHUNK = 2048;  // list entries per CTA in the global-level partition kernels
 
