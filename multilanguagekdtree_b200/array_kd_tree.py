@@ -193,6 +193,32 @@ def leaf_parts(nodes: np.ndarray, indices: np.ndarray, max_parts: int = MAX_PART
     return out
 
 
+def print_tree(step: int, tree: np.ndarray, indices: np.ndarray, particles: np.ndarray, directory: str = ".") -> str:
+    """array_kd_tree.rs:666-692 — write `tree{step}.txt` in the reference's text format (the input of
+    TreeVisualizer/src/main/scala/ViewTrees.scala:32-80): the node count, then per node either `L n` followed by n
+    lines `x y z`, or `I split_dim split_val left right`.  Numbers are printed like Rust's `{}` (shortest decimal
+    that round-trips, never an exponent)."""
+    import os
+
+    def f(x: float) -> str:
+        return np.format_float_positional(float(x), unique=True, trim="-")
+
+    path = os.path.join(directory, f"tree{step}.txt")
+    with open(path, "w") as out:
+        out.write(f"{len(tree)}\n")
+        for nd in tree:
+            if nd["kind"] == INTERNAL:
+                out.write(f"I {int(nd['split_dim'])} {f(nd['split_val'])} {int(nd['left'])} {int(nd['right'])}\n")
+            else:
+                k = int(nd["num_parts"])
+                out.write(f"L {k}\n")
+                first = int(nd["leaf_first"]) if k else 0
+                for i in range(k):
+                    p = particles[int(indices[first + i])]["p"]
+                    out.write(f"{f(p[0])} {f(p[1])} {f(p[2])}\n")
+    return path
+
+
 # ---- the reference's free functions -------------------------------------------------------------------------
 
 def build_tree_par4(indices: np.ndarray, cur_node: int, particles: np.ndarray, nodes: np.ndarray, thread_cnt: int = 1,

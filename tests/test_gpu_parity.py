@@ -349,3 +349,27 @@ def test_full_size_properties_1m(orc):
     assert rel_err(acc, oacc).max() <= ACC_RTOL
     for k, f in enumerate(("node_visits", "accepts", "leaf_visits", "pp")):
         assert np.array_equal(cnt[:, k], ocnt[f]), f
+
+
+def test_print_tree_format_matches_oracle_dump(orc, tmp_path):
+    """array_kd_tree.rs:666-692 / TreeVisualizer reader: same records as the oracle's dump of the same (canonical) tree."""
+    parts = orc.circular_orbits(500, seed=13)
+    with kd.KDTreeSim() as sim:
+        sim.upload(parts)
+        sim.build_tree()
+        nodes, idx = sim.tree()
+    gpath = kd.print_tree(0, nodes, idx, parts, str(tmp_path))
+    onodes, _, _ = orc.build_tree_canonical(parts)
+    opath = str(tmp_path / "oracle_tree0.txt")
+    orc.print_tree(opath, onodes, parts)
+    g, o = open(gpath).read().split("\n"), open(opath).read().split("\n")
+    assert len(g) == len(o) and g[0] == o[0] == str(len(nodes))
+    for lg, lo in zip(g[1:], o[1:]):
+        tg, to = lg.split(), lo.split()
+        assert len(tg) == len(to)
+        for a, b in zip(tg, to):
+            if a in ("L", "I"):
+                assert a == b
+            else:
+                assert float(a) == float(b)          # %.17g there, Rust-style shortest form here: equal as numbers
+                assert "e" not in a.lower()            # Rust's `{}` never prints an exponent
