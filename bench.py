@@ -215,18 +215,29 @@ def run_kdnb(args) -> None:
     stage, nsteps = sim.stage_ms()
     value = (n + 1) * K / (ms * 1e-3)
 
-    # ---- e2e: the reference-facing call with HOST buffers, copies inside the timed region, every step
+    # ---- e2e: the reference-facing call with HOST buffers, copies inside the timed region, every step.
+    # N > 1: every rank owns the slice host_shard_range(n, rank, world) of the host array (sharded host state, as a
+    # multi-process caller would hold it): its PCIe traffic is 1/N of the state, the rest travels over NVLink.
     host[:] = ics
-    sim.simple_sim_bodies(host, DT, 1)                     # warm
+    if world > 1:
+        first, cnt = kd.host_shard_range(n + 1, rank, world)
+        shard = host[first:first + cnt]
+
+        def e2e_call(k):
+            sim.simple_sim_bodies_sharded(shard, n + 1, DT, k)
+    else:
+        def e2e_call(k):
+            sim.simple_sim_bodies(host, DT, k)
+    e2e_call(1)                                             # warm
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        sim.simple_sim_bodies(host, DT, 1)                 # upload 64 B/particle, one step, download 64 B/particle
+        e2e_call(1)                                         # upload 64 B/particle, one step, download 64 B/particle
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     t0 = time.perf_counter()
-    sim.simple_sim_bodies(host, DT, K)                     # the reference's own call shape: simple_sim(bodies, dt, K)
+    e2e_call(K)                                             # the reference's own call shape: simple_sim(bodies, dt, K)
     e2e_amort_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop()
 
@@ -279,7 +290,7 @@ def run_kdnb(args) -> None:
                 "kick": {"bytes_model": kick_bytes, "achieved": kick_bytes / (kick_ms * 1e-3) / 1e9, "frac": kick_bytes / (kick_ms * 1e-3) / 1e9 / hbm_peak},
             },
             "e2e": {"value": (n + 1) * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb,
-                    "note": "K calls of kdnb_simple_sim_bodies(host, dt, 1): pinned-host upload + one step + download per call"},
+                    "note": "K calls of kdnb_simple_sim_bodies[_sharded](host, dt, 1): pinned-host upload + one step + download per call; bytes are the sum over ranks (each rank moves its 1/N host shard over PCIe, NVLink all-gather for the rest)"},
             "e2e_amortized": {"value": (n + 1) * K / e2e_amort_s, "unit": UNIT, "note": "one call simple_sim(bodies, dt, K) with host buffers"},
             "gpu_launches": int(launches), "clocks": clocks,
         }

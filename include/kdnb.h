@@ -131,6 +131,14 @@ int kdnb_shard_range(uint64_t count, int rank, int world_size, uint64_t* begin, 
 int kdnb_comm_unique_id(void* id_out_128_bytes);
 int kdnb_comm_init(kdnb_ctx* ctx, const void* id_128_bytes, int rank, int world_size);
 
+/* Sharded host buffers for multi-GPU callers: rank r owns particles [first, first+count) of the global array
+ * (kdnb_host_shard_range; equal shards of ceil(total/world)).  Upload sends only the own shard over PCIe and
+ * all-gathers the rest over NVLink; download returns only the own shard (every replica holds the full state). */
+int kdnb_host_shard_range(uint64_t total, int rank, int world_size, uint64_t* first, uint64_t* count);
+int kdnb_upload_particles_sharded(kdnb_ctx* ctx, const kdnb_particle* shard, uint64_t total);
+int kdnb_download_particles_sharded(kdnb_ctx* ctx, kdnb_particle* shard_out);
+int kdnb_simple_sim_bodies_sharded(kdnb_ctx* ctx, kdnb_particle* shard, uint64_t total, double dt, int64_t steps);
+
 /* ---- measurement */
 enum { KDNB_STAGE_BUILD = 0, KDNB_STAGE_WALK = 1, KDNB_STAGE_KICK = 2, KDNB_STAGE_EXCHANGE = 3, KDNB_STAGE_COUNT = 4 };
 int kdnb_stage_ms(kdnb_ctx* ctx, double ms_out[KDNB_STAGE_COUNT], uint64_t* steps_out); /* sums since last reset; needs KDNB_FLAG_PROFILE; synchronizes */

@@ -5,6 +5,7 @@ from . import array_kd_tree, array_particle
 from ._lib import (FLAG_EXACT_MATH, FLAG_PROFILE, FLAG_WALK_COUNTS, INTERNAL, LAYOUT_DENSE, LAYOUT_PADDED, LEAF, NODE,
                    NO_INDEX, PARTICLE)
 from .array_kd_tree import (MAX_PARTS, THETA, KDTreeSim, KdnbError, allocate_node_vec, build_tree, build_tree_par4,
+                            host_shard_range,
                             calc_accel_all, leaf_parts, nodes_needed_for_particles, print_tree, shard_range,
                             simple_sim)
 from .array_particle import circular_orbits, two_bodies
@@ -13,5 +14,5 @@ __all__ = [
     "array_kd_tree", "array_particle", "KDTreeSim", "KdnbError", "MAX_PARTS", "THETA", "PARTICLE", "NODE", "LEAF",
     "INTERNAL", "NO_INDEX", "LAYOUT_PADDED", "LAYOUT_DENSE", "FLAG_PROFILE", "FLAG_WALK_COUNTS", "FLAG_EXACT_MATH",
     "allocate_node_vec", "nodes_needed_for_particles", "build_tree", "build_tree_par4", "calc_accel_all", "simple_sim",
-    "leaf_parts", "print_tree", "shard_range", "circular_orbits", "two_bodies",
+    "leaf_parts", "host_shard_range", "print_tree", "shard_range", "circular_orbits", "two_bodies",
 ]

@@ -29,7 +29,8 @@ SYMBOLS = [
     "kdnb_download_particles", "kdnb_particle_count", "kdnb_build_tree", "kdnb_calc_accel", "kdnb_kick_drift",
     "kdnb_simple_sim", "kdnb_simple_sim_host", "kdnb_simple_sim_bodies", "kdnb_synchronize", "kdnb_download_accel",
     "kdnb_upload_accel", "kdnb_download_tree", "kdnb_download_walk_counts", "kdnb_nodes_needed", "kdnb_node_count",
-    "kdnb_shard_range", "kdnb_comm_unique_id", "kdnb_comm_init", "kdnb_stage_ms", "kdnb_stage_reset", "kdnb_launch_count",
+    "kdnb_shard_range", "kdnb_host_shard_range", "kdnb_upload_particles_sharded",
+    "kdnb_download_particles_sharded", "kdnb_simple_sim_bodies_sharded", "kdnb_comm_unique_id", "kdnb_comm_init", "kdnb_stage_ms", "kdnb_stage_reset", "kdnb_launch_count",
     "kdnb_measure_fp64_peak", "kdnb_flush_l2", "kdnb_device_ms", "kdnb_host_alloc", "kdnb_host_free",
 ]
 
@@ -79,6 +80,14 @@ def load() -> C.CDLL:
     L.kdnb_node_count.argtypes = [vp]
     L.kdnb_shard_range.argtypes = [u64, i32, i32, vp, vp]
     L.kdnb_shard_range.restype = i32
+    L.kdnb_host_shard_range.argtypes = [u64, i32, i32, vp, vp]
+    L.kdnb_host_shard_range.restype = i32
+    L.kdnb_upload_particles_sharded.argtypes = [vp, vp, u64]
+    L.kdnb_upload_particles_sharded.restype = i32
+    L.kdnb_download_particles_sharded.argtypes = [vp, vp]
+    L.kdnb_download_particles_sharded.restype = i32
+    L.kdnb_simple_sim_bodies_sharded.argtypes = [vp, vp, u64, f64, i64]
+    L.kdnb_simple_sim_bodies_sharded.restype = i32
     L.kdnb_comm_unique_id.argtypes = [vp]
     L.kdnb_comm_init.argtypes = [vp, vp, i32, i32]
     L.kdnb_stage_ms.argtypes = [vp, vp, vp]
@@ -94,7 +103,8 @@ def load() -> C.CDLL:
     for fn in ("kdnb_upload_particles", "kdnb_download_particles", "kdnb_build_tree", "kdnb_calc_accel", "kdnb_kick_drift",
                "kdnb_simple_sim", "kdnb_simple_sim_host", "kdnb_simple_sim_bodies", "kdnb_synchronize",
                "kdnb_download_accel", "kdnb_upload_accel", "kdnb_download_tree", "kdnb_download_walk_counts",
-               "kdnb_shard_range", "kdnb_comm_unique_id", "kdnb_comm_init", "kdnb_stage_ms", "kdnb_stage_reset", "kdnb_measure_fp64_peak",
+               "kdnb_shard_range", "kdnb_host_shard_range", "kdnb_upload_particles_sharded",
+    "kdnb_download_particles_sharded", "kdnb_simple_sim_bodies_sharded", "kdnb_comm_unique_id", "kdnb_comm_init", "kdnb_stage_ms", "kdnb_stage_reset", "kdnb_measure_fp64_peak",
                "kdnb_flush_l2", "kdnb_device_ms"):
         getattr(L, fn).restype = i32
     _lib = L

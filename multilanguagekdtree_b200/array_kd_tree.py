@@ -43,6 +43,15 @@ def shard_range(count: int, rank: int, world: int):
     return int(b.value), int(e.value)
 
 
+def host_shard_range(total: int, rank: int, world: int):
+    """Slice [first, first+count) of the global particle array that rank `rank` keeps on the host (kdnb_host_shard_range)."""
+    f, n = C.c_uint64(0), C.c_uint64(0)
+    rc = _lib.load().kdnb_host_shard_range(total, rank, world, C.byref(f), C.byref(n))
+    if rc != 0:
+        raise KdnbError(f"kdnb_host_shard_range rc={rc}")
+    return int(f.value), int(n.value)
+
+
 class KDTreeSim:
     """One GPU context: owns what `simple_sim` owns (acc, tree, indices; array_kd_tree.rs:624-630)."""
 
@@ -109,6 +118,11 @@ class KDTreeSim:
     def simple_sim_bodies(self, bodies: np.ndarray, dt: float, steps: int) -> None:
         assert bodies.dtype == PARTICLE and bodies.flags.c_contiguous
         self._ck(self._L.kdnb_simple_sim_bodies(self._h, bodies.ctypes.data, len(bodies), dt, steps), "kdnb_simple_sim_bodies")
+
+    def simple_sim_bodies_sharded(self, shard: np.ndarray, total: int, dt: float, steps: int) -> None:
+        """Multi-GPU form: `shard` is this rank's slice host_shard_range(total, rank, world) of the global bodies."""
+        assert shard.dtype == PARTICLE and shard.flags.c_contiguous
+        self._ck(self._L.kdnb_simple_sim_bodies_sharded(self._h, shard.ctypes.data, total, dt, steps), "kdnb_simple_sim_bodies_sharded")
 
     def synchronize(self) -> None:
         self._ck(self._L.kdnb_synchronize(self._h), "kdnb_synchronize")

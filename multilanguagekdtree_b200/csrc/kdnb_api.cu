@@ -62,6 +62,7 @@ bool load_nccl(std::string* why) {
   return g_nccl.handle != nullptr;
 }
 constexpr int NCCL_FLOAT64 = 8;  // ncclDouble
+constexpr int NCCL_UINT8 = 1;
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -150,7 +151,7 @@ static int plan(Ctx* c, uint64_t n) {
     }
     if (!rc) rc = dev_alloc(c, &c->mass, n);
     if (!rc) rc = dev_alloc(c, &c->radius, n);
-    if (!rc) rc = dev_alloc(c, &c->aos, std::max<uint64_t>(n, (c->n_nodes * sizeof(kdnb_node) + 63) / 64));
+    if (!rc) rc = dev_alloc(c, &c->aos, std::max<uint64_t>(n + 64, (c->n_nodes * sizeof(kdnb_node) + 63) / 64));  // +64: padded host shards
     if (!rc) rc = dev_alloc(c, &c->keys[0], 3 * n);
     if (!rc) rc = dev_alloc(c, &c->keys[1], 3 * n);
     if (!rc) rc = dev_alloc(c, &c->list[0], 3 * n);
@@ -352,6 +353,50 @@ int kdnb_simple_sim(kdnb_ctx* ctx, double dt, int64_t steps) {
   for (int64_t s = 0; s < steps; ++s)
     if (int rc = one_step(c, dt)) return rc;
   return 0;
+}
+
+// ---- sharded host buffers (multi-GPU): rank r holds particles [first, first+shard) of the global array
+static uint64_t host_shard(uint64_t total, int world) { return (total + world - 1) / world; }
+
+int kdnb_host_shard_range(uint64_t total, int rank, int world_size, uint64_t* first, uint64_t* count) {
+  if (world_size < 1 || rank < 0 || rank >= world_size || !first || !count) return KDNB_E_INVALID;
+  const uint64_t s = host_shard(total, world_size);
+  *first = std::min<uint64_t>(total, (uint64_t)rank * s);
+  *count = std::min<uint64_t>(total, (uint64_t)(rank + 1) * s) - *first;
+  return 0;
+}
+
+int kdnb_upload_particles_sharded(kdnb_ctx* ctx, const kdnb_particle* shard, uint64_t total) {
+  CTX_OR_FAIL(ctx);
+  if (c->world <= 1) return kdnb_upload_particles(ctx, shard, total);
+  if (!shard) return c->fail(KDNB_E_INVALID, "null particle array");
+  if (int rc = plan(c, total)) return rc;
+  const uint64_t s = host_shard(total, c->world);
+  uint64_t first = 0, cnt = 0;
+  kdnb_host_shard_range(total, c->rank_id, c->world, &first, &cnt);
+  // own shard over PCIe, everybody else's over NVLink (in-place ncclAllGather of equal, padded shards)
+  if (cnt) KDNB_CUDA_TRY(c, cudaMemcpyAsync(c->aos + (size_t)c->rank_id * s, shard, cnt * sizeof(kdnb_particle), cudaMemcpyHostToDevice, c->stream));
+  int r = g_nccl.all_gather(c->aos + (size_t)c->rank_id * s, c->aos, s * sizeof(kdnb_particle), NCCL_UINT8, c->nccl_comm, c->stream);
+  if (r != 0) return c->fail(KDNB_E_NCCL, "ncclAllGather(particles) failed");
+  return aos_to_soa(c);
+}
+
+int kdnb_download_particles_sharded(kdnb_ctx* ctx, kdnb_particle* shard_out) {
+  CTX_OR_FAIL(ctx);
+  if (!shard_out) return c->fail(KDNB_E_INVALID, "null output array");
+  if (c->n == 0) return c->fail(KDNB_E_INVALID, "no particles uploaded");
+  uint64_t first = 0, cnt = 0;
+  kdnb_host_shard_range(c->n, c->rank_id, c->world, &first, &cnt);
+  if (int rc = soa_to_aos(c)) return rc;  // every replica holds the full, bit-identical state
+  if (cnt) KDNB_CUDA_TRY(c, cudaMemcpyAsync(shard_out, c->aos + first, cnt * sizeof(kdnb_particle), cudaMemcpyDeviceToHost, c->stream));
+  KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int kdnb_simple_sim_bodies_sharded(kdnb_ctx* ctx, kdnb_particle* shard, uint64_t total, double dt, int64_t steps) {
+  if (int rc = kdnb_upload_particles_sharded(ctx, shard, total)) return rc;
+  if (int rc = kdnb_simple_sim(ctx, dt, steps)) return rc;
+  return kdnb_download_particles_sharded(ctx, shard);
 }
 
 int kdnb_simple_sim_bodies(kdnb_ctx* ctx, kdnb_particle* bodies, uint64_t count, double dt, int64_t steps) {

@@ -35,6 +35,11 @@ def main():
     acc = sim.accel()
     sim.simple_sim(1e-3, steps)
     out = sim.download()
+    # sharded host buffers: upload own shard + NVLink all-gather, run, download own shard
+    first, cnt = kd.host_shard_range(n + 1, rank, world)
+    shard = ics[first:first + cnt].copy()
+    sim.simple_sim_bodies_sharded(shard, n + 1, 1e-3, steps)
+    assert shard.tobytes() == out[first:first + cnt].tobytes(), "sharded host path differs from the replicated path"
     sim.close()
     blobs = [None] * world
     dist.all_gather_object(blobs, (out.tobytes(), acc.tobytes()))
