@@ -73,6 +73,12 @@ struct Ctx {
   void* nccl_comm = nullptr;
   uint64_t shard_slots = 0;  // tree slots per rank (multiple of 32)
 
+  // one step captured as a CUDA graph (replayed by kdnb_simple_sim when not profiling)
+  cudaGraphExec_t step_graph = nullptr;
+  uint64_t graph_n = 0, graph_launches = 0;
+  double graph_dt = 0.0;
+  int graph_world = 0;
+
   // measurement
   uint64_t launches = 0;
   std::vector<cudaEvent_t> ev;  // 5 events per profiled step

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -120,6 +121,12 @@ static void free_all(Ctx* c) {
   fr(c->tmp3);
 }
 
+static void drop_graph_if_any(Ctx* c) {
+  if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
+  c->step_graph = nullptr;
+  c->graph_n = 0;
+}
+
 static uint64_t padded_slots(uint64_t n) { return n + 64ull * 64ull; }
 // tree slots per rank: equal, warp-group aligned (64 = 32 lanes x 2 particles per lane) so that shards never split a warp
 static uint64_t shard_slots_for(uint64_t n, int world) { return (((n + world - 1) / world) + 63) / 64 * 64; }
@@ -139,6 +146,7 @@ static int plan(Ctx* c, uint64_t n) {
   const uint64_t chunks = 3ull * (n / LVL_CHUNK + table + 8);
   const bool grow = n > c->cap || c->n_nodes > c->node_cap || table > c->table_cap || chunks > c->chunk_cap;
   if (grow) {
+    drop_graph_if_any(c);
     free_all(c);
     c->cap = n;
     c->node_cap = c->n_nodes;
@@ -291,6 +299,7 @@ void kdnb_destroy(kdnb_ctx* ctx) {
   Ctx* c = &ctx->c;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  drop_graph_if_any(c);
   if (c->nccl_comm && g_nccl.comm_destroy) g_nccl.comm_destroy(c->nccl_comm);
   free_all(c);
   if (c->l2_scratch) cudaFree(c->l2_scratch);
@@ -347,10 +356,54 @@ int kdnb_kick_drift(kdnb_ctx* ctx, double dt) {
   return kick_drift(c, dt);
 }
 
+static void drop_graph(Ctx* c) {
+  if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
+  c->step_graph = nullptr;
+  c->graph_n = 0;
+}
+
 int kdnb_simple_sim(kdnb_ctx* ctx, double dt, int64_t steps) {
   CTX_OR_FAIL(ctx);
   if (c->n == 0) return c->fail(KDNB_E_INVALID, "no particles uploaded");
-  for (int64_t s = 0; s < steps; ++s)
+  int64_t s = 0;
+  // Launch-bound regime (N <= ~1M: ~60 kernels of 5-35 us per step): replay the step as one CUDA graph.  The first
+  // step of a call always runs as plain launches (lazy one-time setup: function attributes, NCCL connections).
+  static const bool no_graph = getenv("KDNB_NO_GRAPH") != nullptr;
+  const bool use_graph = !(c->flags & KDNB_FLAG_PROFILE) && !no_graph && steps >= 3;
+  if (use_graph) {
+    if (int rc = one_step(c, dt)) return rc;
+    s = 1;
+    if (!c->step_graph || c->graph_n != c->n || c->graph_dt != dt || c->graph_world != c->world) {
+      drop_graph(c);
+      const uint64_t l0 = c->launches;
+      KDNB_CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = one_step(c, dt);
+      cudaGraph_t g = nullptr;
+      cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+      c->graph_launches = c->launches - l0;
+      c->launches = l0;  // the capture launched nothing
+      if (rc || e != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        if (rc) return rc;
+        return c->fail(KDNB_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+      }
+      e = cudaGraphInstantiate(&c->step_graph, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess) {
+        c->step_graph = nullptr;
+        return c->fail(KDNB_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+      }
+      c->graph_n = c->n;
+      c->graph_dt = dt;
+      c->graph_world = c->world;
+    }
+    for (; s < steps; ++s) {
+      KDNB_CUDA_TRY(c, cudaGraphLaunch(c->step_graph, c->stream));
+      c->launches += c->graph_launches;
+    }
+    return 0;
+  }
+  for (; s < steps; ++s)
     if (int rc = one_step(c, dt)) return rc;
   return 0;
 }
