@@ -35,15 +35,19 @@ __global__ void build_root(uint32_t* tstart, uint32_t* tlen, uint32_t* tnode, ui
   tnode[0] = 0;
 }
 
-__global__ void __launch_bounds__(128) level_stats(Pos3c pos, Lists L, int level, uint32_t mp, int layout,
-                                                   uint32_t* __restrict__ tstart, uint32_t* __restrict__ tlen,
-                                                   uint32_t* __restrict__ tnode, uint32_t* __restrict__ tmid,
-                                                   uint8_t* __restrict__ tsd, WNode* __restrict__ nodes,
-                                                   const uint32_t* __restrict__ flat, const uint32_t* __restrict__ rk,
-                                                   uint32_t n, uint32_t* __restrict__ tmr) {
+// Statistics of segment s of `level` (bbox from the list ends, split dimension, median).  Every CTA working on the
+// segment evaluates this (a handful of gathers); the one flagged `writer` also emits the node record and the table
+// entries of the two children.  Returns sd, mid and the initial rank of the median element.
+struct SegStats {
+  uint32_t a, len, sd, mid, rmid;
+};
+__device__ __forceinline__ SegStats seg_stats(Pos3c pos, Lists L, int level, uint32_t s, uint32_t mp, int layout,
+                                              uint32_t* __restrict__ tstart, uint32_t* __restrict__ tlen,
+                                              uint32_t* __restrict__ tnode, uint32_t* __restrict__ tmid,
+                                              uint8_t* __restrict__ tsd, WNode* __restrict__ nodes,
+                                              const uint32_t* __restrict__ flat, const uint32_t* __restrict__ rk,
+                                              uint32_t n, uint32_t* __restrict__ tmr, bool writer) {
   const uint32_t nseg = 1u << level;
-  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nseg) return;
   const uint32_t off = nseg - 1;
   const uint32_t a = tstart[off + s], len = tlen[off + s], node = tnode[off + s];
   double mn[3], mx[3];
@@ -67,44 +71,55 @@ __global__ void __launch_bounds__(128) level_stats(Pos3c pos, Lists L, int level
   }
   const uint32_t half = len / 2, mid = a + half;
   const uint32_t mid_id = L.l[sd][mid];
-  const double split_val = pos.p[sd][mid_id];
-  const uint32_t nleft = (uint32_t)subtree_nodes(half, mp, layout);
-  WNode* nd = &nodes[node];
-  nd->size2 = __dmul_rn(ext, ext);
-  nd->size = ext;
-  nd->split_val = split_val;
-  nd->a = node + 1 + nleft;
-  nd->b = WN_INTERNAL | (uint32_t)sd;
-  tsd[off + s] = (uint8_t)sd;
-  tmid[off + s] = mid;
-  tmr[off + s] = rk[(uint64_t)sd * n + mid_id];
-  const uint32_t coff = 2 * nseg - 1;
-  tstart[coff + 2 * s] = a;
-  tlen[coff + 2 * s] = half;
-  tnode[coff + 2 * s] = node + 1;
-  tstart[coff + 2 * s + 1] = mid;
-  tlen[coff + 2 * s + 1] = len - half;
-  tnode[coff + 2 * s + 1] = node + 1 + nleft;
+  SegStats r;
+  r.a = a;
+  r.len = len;
+  r.sd = (uint32_t)sd;
+  r.mid = mid;
+  r.rmid = rk[(uint64_t)sd * n + mid_id];
+  if (writer) {
+    const double split_val = pos.p[sd][mid_id];
+    const uint32_t nleft = (uint32_t)subtree_nodes(half, mp, layout);
+    WNode* nd = &nodes[node];
+    nd->size2 = __dmul_rn(ext, ext);
+    nd->size = ext;
+    nd->split_val = split_val;
+    nd->a = node + 1 + nleft;
+    nd->b = WN_INTERNAL | (uint32_t)sd;
+    tsd[off + s] = (uint8_t)sd;
+    tmid[off + s] = mid;
+    tmr[off + s] = r.rmid;
+    const uint32_t coff = 2 * nseg - 1;
+    tstart[coff + 2 * s] = a;
+    tlen[coff + 2 * s] = half;
+    tnode[coff + 2 * s] = node + 1;
+    tstart[coff + 2 * s + 1] = mid;
+    tlen[coff + 2 * s + 1] = len - half;
+    tnode[coff + 2 * s + 1] = node + 1 + nleft;
+  }
+  return r;
 }
 
 // "goes left" is decided without any per-level flag pass: rk[d][id] is the rank of particle id in the INITIAL sorted
 // list of dimension d (sort.cu).  Stable partitions keep every segment of list d ordered by rk[d], so the left half of
 // a node split along sd is exactly { id : rk[sd][id] < rk[sd][id of the element at mid] } (tmr[] holds that rank).
-__global__ void __launch_bounds__(LVL_THREADS) level_count(Lists L, int level, uint32_t cps,
-                                                           const uint32_t* __restrict__ tstart,
-                                                           const uint32_t* __restrict__ tlen,
-                                                           const uint8_t* __restrict__ tsd,
-                                                           const uint32_t* __restrict__ rk, uint32_t n,
-                                                           const uint32_t* __restrict__ tmr,
-                                                           uint32_t* __restrict__ cnt,
-                                                           const uint32_t* __restrict__ flat) {
+__global__ void __launch_bounds__(LVL_THREADS)
+level_count(Pos3c pos, Lists L, int level, uint32_t cps, uint32_t mp, int layout, uint32_t* __restrict__ tstart,
+            uint32_t* __restrict__ tlen, uint32_t* __restrict__ tnode, uint32_t* __restrict__ tmid,
+            uint8_t* __restrict__ tsd, WNode* __restrict__ nodes, const uint32_t* __restrict__ rk, uint32_t n,
+            uint32_t* __restrict__ tmr, uint32_t* __restrict__ cnt, const uint32_t* __restrict__ flat) {
   __shared__ uint32_t wsum[LVL_THREADS / 32];
+  __shared__ SegStats st;
   const uint32_t seg = blockIdx.x / cps, chunk = blockIdx.x % cps, e = blockIdx.y;
-  const uint32_t nseg = 1u << level, off = nseg - 1;
-  if (tsd[off + seg] == e || flat[e]) return;  // the split-dimension list is already partitioned; flat lists are unused
-  const uint32_t a = tstart[off + seg], len = tlen[off + seg], rmid = tmr[off + seg];
+  const uint32_t nseg = 1u << level;
+  if (threadIdx.x == 0)
+    st = seg_stats(pos, L, level, seg, mp, layout, tstart, tlen, tnode, tmid, tsd, nodes, flat, rk, n, tmr,
+                   chunk == 0 && e == 0);
+  __syncthreads();
+  if (st.sd == e || flat[e]) return;  // the split-dimension list is already partitioned; flat lists are unused
+  const uint32_t a = st.a, len = st.len, rmid = st.rmid;
   const uint32_t* lst = L.l[e];
-  const uint32_t* rks = rk + (uint64_t)tsd[off + seg] * n;
+  const uint32_t* rks = rk + (uint64_t)st.sd * n;
   uint32_t c = 0;
 #pragma unroll
   for (int k = 0; k < LVL_CHUNK / LVL_THREADS; ++k) {
@@ -530,10 +545,8 @@ int build_tree(Ctx* c) {
     const uint32_t cps = (maxlen + LVL_CHUNK - 1) / LVL_CHUNK;
     Lists Lin = {{c->list[cur], c->list[cur] + n, c->list[cur] + 2ull * n}};
     Lists Lout = {{c->list[cur ^ 1], c->list[cur ^ 1] + n, c->list[cur ^ 1] + 2ull * n}};
-    KDNB_LAUNCH(c, level_stats, (nseg + 127) / 128, 128, 0, pos, Lin, lev, c->mp, c->layout, c->tstart, c->tlen,
-                c->tnode, c->tmid, c->tsd, c->nodes, c->flat, c->rk, n, c->tmr);
-    KDNB_LAUNCH(c, level_count, dim3(nseg * cps, 3), LVL_THREADS, 0, Lin, lev, cps, c->tstart, c->tlen, c->tsd,
-                c->rk, n, c->tmr, c->chunk_cnt, c->flat);
+    KDNB_LAUNCH(c, level_count, dim3(nseg * cps, 3), LVL_THREADS, 0, pos, Lin, lev, cps, c->mp, c->layout, c->tstart,
+                c->tlen, c->tnode, c->tmid, c->tsd, c->nodes, c->rk, n, c->tmr, c->chunk_cnt, c->flat);
     KDNB_LAUNCH(c, level_scatter, dim3(nseg * cps, 3), LVL_THREADS, 0, Lin, Lout, lev, cps, c->tstart, c->tlen,
                 c->tmid, c->tsd, c->rk, n, c->tmr, c->chunk_cnt, c->flat);
     cur ^= 1;
