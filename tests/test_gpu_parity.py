@@ -373,3 +373,19 @@ def test_print_tree_format_matches_oracle_dump(orc, tmp_path):
             else:
                 assert float(a) == float(b)          # %.17g there, Rust-style shortest form here: equal as numbers
                 assert "e" not in a.lower()            # Rust's `{}` never prints an exponent
+
+
+def test_graph_replay_equals_plain_launches(orc):
+    """kdnb_simple_sim replays the step as a CUDA graph for calls of >= 3 steps; shorter calls use plain launches.
+    Both must give bit-identical trajectories."""
+    parts = orc.circular_orbits(30000, seed=5)
+    with kd.KDTreeSim() as a, kd.KDTreeSim() as b:
+        a.upload(parts)
+        b.upload(parts)
+        a.simple_sim(1e-3, 8)            # 1 plain step + 7 graph replays
+        for _ in range(4):
+            b.simple_sim(1e-3, 2)        # plain launches only
+        assert a.download().tobytes() == b.download().tobytes()
+        a.simple_sim(1e-3, 5)            # graph reused
+        b.simple_sim(1e-3, 2); b.simple_sim(1e-3, 2); b.simple_sim(1e-3, 1)
+        assert a.download().tobytes() == b.download().tobytes()
