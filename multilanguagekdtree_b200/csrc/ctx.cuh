@@ -13,6 +13,20 @@ constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // keys per CTA
 constexpr int LVL_THREADS = 256;
 constexpr int LVL_CHUNK = 2048;  // list entries per CTA in the global-level partition kernels
 
+// Peer-memory exchange (multi-GPU): every rank's walk kernel stores its accelerations straight into all peers'
+// acc_t buffers over NVLink (cudaIpc-mapped), then raises a per-rank flag on every peer; a one-CTA wait kernel on each
+// GPU spins on its local flags.  Two acc buffers alternate by step parity so a fast rank never overwrites a buffer a
+// slow rank is still consuming.
+constexpr int P2P_MAX = 16;
+struct P2P {
+  double* acc[P2P_MAX];      // peers' acc_t bases, own included
+  uint32_t* flags[P2P_MAX];  // peers' flag arrays [P2P_MAX]
+  const uint32_t* epoch;     // local step counter (device)
+  uint32_t* cta_done;        // local "CTAs finished" counter (device)
+  uint64_t stride;           // doubles between the two acc buffers
+  int world, rank;
+};
+
 struct Ctx {
   // configuration
   int device = 0;
@@ -72,6 +86,12 @@ struct Ctx {
   int rank_id = 0, world = 1;
   void* nccl_comm = nullptr;
   uint64_t shard_slots = 0;  // tree slots per rank (multiple of 32)
+  bool p2p_ready = false;    // peer set-up attempted for the current allocation
+  bool p2p_on = false;       // accelerations exchanged by peer stores inside the walk kernel (else ncclAllGather)
+  P2P p2p = {};
+  uint32_t* p2p_state = nullptr;  // device: [0] epoch, [1] cta_done, [2] error, [4..4+P2P_MAX) flags
+  void* p2p_mapped[2 * P2P_MAX] = {};
+  uint64_t acc_stride = 0;   // doubles per acc buffer
 
   // one step captured as a CUDA graph (replayed by kdnb_simple_sim when not profiling)
   cudaGraphExec_t step_graph = nullptr;
@@ -103,6 +123,7 @@ void init_unused_nodes(Ctx* c);
 int walk(Ctx* c);
 // kick.cu
 int kick_drift(Ctx* c, double dt);
+int p2p_wait_step(Ctx* c);
 int aos_to_soa(Ctx* c);
 int soa_to_aos(Ctx* c);
 int gather_acc(Ctx* c, double* dst_orig_order);

@@ -83,6 +83,8 @@ static int dev_alloc(Ctx* c, T** p, uint64_t count) {
   return 0;
 }
 
+static void close_peers(Ctx* c);
+
 static void free_all(Ctx* c) {
   auto fr = [](auto*& p) {
     if (p) cudaFree(p);
@@ -116,9 +118,101 @@ static void free_all(Ctx* c) {
   fr(c->perm);
   fr(c->rank);
   c->posm = nullptr;  // lives inside the nodes allocation
+  close_peers(c);
   fr(c->acc_t);
+  fr(c->p2p_state);
   fr(c->wcounts);
   fr(c->tmp3);
+}
+
+// ---- peer-memory exchange set-up: cudaIpc handles of acc_t and of the flag array, all-gathered with NCCL
+static void close_peers(Ctx* c) {
+  for (int i = 0; i < 2 * P2P_MAX; ++i) {
+    if (c->p2p_mapped[i]) cudaIpcCloseMemHandle(c->p2p_mapped[i]);
+    c->p2p_mapped[i] = nullptr;
+  }
+  c->p2p_on = false;
+  c->p2p_ready = false;
+}
+
+static int setup_peers(Ctx* c) {
+  close_peers(c);
+  c->p2p_ready = true;  // attempted for this allocation (success or not)
+  static const bool disabled = getenv("KDNB_NO_P2P") != nullptr;
+  const int W = c->world;
+  KDNB_CUDA_TRY(c, cudaMemsetAsync(c->p2p_state, 0, (4 + P2P_MAX) * sizeof(uint32_t), c->stream));
+  // every rank must take the same decision: exchange {ok, handle(acc), handle(state)} records
+  struct Rec {
+    int ok;
+    int pad[15];
+    cudaIpcMemHandle_t acc, st;
+  };
+  static_assert(sizeof(Rec) == 192, "Rec");
+  Rec mine;
+  memset(&mine, 0, sizeof mine);
+  mine.ok = (!disabled && W <= P2P_MAX) ? 1 : 0;
+  if (mine.ok && cudaIpcGetMemHandle(&mine.acc, c->acc_t) != cudaSuccess) mine.ok = 0;
+  if (mine.ok && cudaIpcGetMemHandle(&mine.st, c->p2p_state) != cudaSuccess) mine.ok = 0;
+  cudaGetLastError();
+  Rec* dev = nullptr;
+  KDNB_CUDA_TRY(c, cudaMalloc(&dev, sizeof(Rec) * W));
+  KDNB_CUDA_TRY(c, cudaMemcpyAsync(dev + c->rank_id, &mine, sizeof(Rec), cudaMemcpyHostToDevice, c->stream));
+  int r = g_nccl.all_gather(dev + c->rank_id, dev, sizeof(Rec), NCCL_UINT8, c->nccl_comm, c->stream);
+  std::vector<Rec> all(W);
+  cudaError_t e = cudaMemcpyAsync(all.data(), dev, sizeof(Rec) * W, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(dev);
+  if (r != 0) return c->fail(KDNB_E_NCCL, "ncclAllGather(ipc handles) failed");
+  if (e != cudaSuccess) return c->fail(KDNB_E_CUDA, std::string("ipc handle exchange: ") + cudaGetErrorString(e));
+  bool ok = true;
+  for (int k = 0; k < W; ++k) ok = ok && all[k].ok;
+  P2P pp;
+  memset(&pp, 0, sizeof pp);
+  for (int k = 0; ok && k < W; ++k) {
+    if (k == c->rank_id) {
+      pp.acc[k] = c->acc_t;
+      pp.flags[k] = c->p2p_state + 4;
+      continue;
+    }
+    void *pa = nullptr, *ps = nullptr;
+    if (cudaIpcOpenMemHandle(&pa, all[k].acc, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&ps, all[k].st, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      ok = false;
+      if (pa) cudaIpcCloseMemHandle(pa);
+      cudaGetLastError();
+      break;
+    }
+    c->p2p_mapped[2 * k] = pa;
+    c->p2p_mapped[2 * k + 1] = ps;
+    pp.acc[k] = reinterpret_cast<double*>(pa);
+    pp.flags[k] = reinterpret_cast<uint32_t*>(ps) + 4;
+  }
+  // second round: peer mode only if EVERY rank mapped every peer (otherwise all fall back to ncclAllGather)
+  int* dev2 = nullptr;
+  KDNB_CUDA_TRY(c, cudaMalloc(&dev2, sizeof(int) * W));
+  int okv = ok ? 1 : 0;
+  KDNB_CUDA_TRY(c, cudaMemcpyAsync(dev2 + c->rank_id, &okv, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  r = g_nccl.all_gather(dev2 + c->rank_id, dev2, sizeof(int), NCCL_UINT8, c->nccl_comm, c->stream);
+  std::vector<int> oks(W);
+  e = cudaMemcpyAsync(oks.data(), dev2, sizeof(int) * W, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(dev2);
+  if (r != 0 || e != cudaSuccess) return c->fail(KDNB_E_NCCL, "peer set-up vote failed");
+  for (int k = 0; k < W; ++k) ok = ok && oks[k];
+  if (!ok) {
+    const bool keep = c->p2p_ready;
+    close_peers(c);
+    c->p2p_ready = keep;
+    return 0;  // NCCL exchange
+  }
+  pp.epoch = c->p2p_state;
+  pp.cta_done = c->p2p_state + 1;
+  pp.stride = c->acc_stride;
+  pp.world = W;
+  pp.rank = c->rank_id;
+  c->p2p = pp;
+  c->p2p_on = true;
+  return 0;
 }
 
 static void drop_graph_if_any(Ctx* c) {
@@ -182,7 +276,8 @@ static int plan(Ctx* c, uint64_t n) {
     if (!rc) rc = dev_alloc(c, &c->perm, n);
     if (!rc) rc = dev_alloc(c, &c->rank, n);
     if (!rc) c->posm = reinterpret_cast<PosM*>(c->nodes + c->n_nodes);
-    if (!rc) rc = dev_alloc(c, &c->acc_t, 3 * padded_slots(n));
+    if (!rc) rc = dev_alloc(c, &c->acc_t, 2 * 3 * padded_slots(n));  // two buffers: peer exchange alternates by step parity
+    if (!rc) rc = dev_alloc(c, &c->p2p_state, 4 + P2P_MAX);
     if (!rc && (c->flags & KDNB_FLAG_WALK_COUNTS)) rc = dev_alloc(c, &c->wcounts, 4 * n);
     if (!rc) rc = dev_alloc(c, &c->tmp3, 4 * n);
     if (rc) {
@@ -194,16 +289,23 @@ static int plan(Ctx* c, uint64_t n) {
   }
   c->posm = reinterpret_cast<PosM*>(c->nodes + c->n_nodes);
   if (grow || c->planned_n != n) {
-    KDNB_CUDA_TRY(c, cudaMemsetAsync(c->acc_t, 0, 3 * padded_slots(n) * sizeof(double), c->stream));
+    KDNB_CUDA_TRY(c, cudaMemsetAsync(c->acc_t, 0, 2 * 3 * padded_slots(n) * sizeof(double), c->stream));
     init_unused_nodes(c);  // slots the build never writes keep the reference's default Leaf{0, NEGS}
     c->planned_n = n;
   }
-  if (c->world > 1) c->shard_slots = shard_slots_for(n, c->world);
+  c->acc_stride = 3 * padded_slots(c->cap);
+  if (c->world > 1) {
+    c->shard_slots = shard_slots_for(n, c->world);
+    if (grow || !c->p2p_ready) {
+      if (int rc = setup_peers(c)) return rc;
+    }
+  }
   return 0;
 }
 
 static int exchange(Ctx* c) {
   if (c->world <= 1) return 0;
+  if (c->p2p_on) return p2p_wait_step(c);  // the walk kernel already stored into every peer: wait for all flags
   const size_t count = (size_t)c->shard_slots * 3;
   int r = g_nccl.all_gather(c->acc_t + (size_t)c->rank_id * count, c->acc_t, count, NCCL_FLOAT64, c->nccl_comm, c->stream);
   if (r != 0)
@@ -575,7 +677,11 @@ int kdnb_comm_init(kdnb_ctx* ctx, const void* id_bytes, int rank, int world_size
   c->nccl_comm = comm;
   c->rank_id = rank;
   c->world = world_size;
-  if (c->n) c->shard_slots = shard_slots_for(c->n, c->world);
+  if (c->n) {
+    c->shard_slots = shard_slots_for(c->n, c->world);
+    c->acc_stride = 3 * padded_slots(c->cap);
+    if (int rc2 = setup_peers(c)) return rc2;
+  }
   return 0;
 }
 

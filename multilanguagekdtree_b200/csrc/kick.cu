@@ -10,13 +10,32 @@ struct V3 {
   double* p[3];
 };
 
+// which acc buffer holds the accelerations of the step being consumed: peer mode alternates two buffers by step
+// parity (walk wrote buffer epoch&1, the wait kernel then incremented epoch); otherwise there is one buffer
+struct AccSel {
+  double* base;
+  const uint32_t* epoch;  // nullptr: single buffer
+  uint64_t stride;
+};
+__device__ __forceinline__ double* acc_buf(const AccSel& a) {
+  return a.epoch ? a.base + (uint64_t)((*a.epoch + 1u) & 1u) * a.stride : a.base;
+}
+static AccSel acc_sel(const Ctx* c) {
+  AccSel a;
+  a.base = c->acc_t;
+  a.epoch = c->p2p_on ? c->p2p_state : nullptr;
+  a.stride = c->acc_stride;
+  return a;
+}
+
 // thread i = particle i (original order); its acceleration lives at tree slot rank[i]
 __global__ void __launch_bounds__(256) kick_drift_kernel(uint32_t n, double dt, V3 pos, V3 vel,
-                                                         const uint32_t* __restrict__ rank,
-                                                         const double* __restrict__ acc_t, PosM* __restrict__ pm) {
+                                                         const uint32_t* __restrict__ rank, AccSel sel,
+                                                         PosM* __restrict__ pm) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t j = rank[i];
+  double* acc_t = acc_buf(sel);
   const double a0 = acc_t[3 * j + 0], a1 = acc_t[3 * j + 1], a2 = acc_t[3 * j + 2];
   const double v0 = __dadd_rn(vel.p[0][i], __dmul_rn(dt, a0));  // b.v[k] += dt * a[k]   (:650-652)
   const double v1 = __dadd_rn(vel.p[1][i], __dmul_rn(dt, a1));
@@ -35,13 +54,23 @@ __global__ void __launch_bounds__(256) kick_drift_kernel(uint32_t n, double dt, 
   pm[i].z = z;
 }
 
+// a[k] = 0 (:659-661), coalesced over the buffer the kick just consumed
+__global__ void __launch_bounds__(256) zero_acc_kernel(AccSel sel, uint64_t count) {
+  double* acc_t = acc_buf(sel);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+    acc_t[i] = 0.0;
+}
+
 int kick_drift(Ctx* c, double dt) {
   const uint32_t n = (uint32_t)c->n;
   V3 pos = {{c->pos[0], c->pos[1], c->pos[2]}}, vel = {{c->vel[0], c->vel[1], c->vel[2]}};
-  KDNB_LAUNCH(c, kick_drift_kernel, (n + 255) / 256, 256, 0, n, dt, pos, vel, c->rank, c->acc_t, c->pm);
+  KDNB_LAUNCH(c, kick_drift_kernel, (n + 255) / 256, 256, 0, n, dt, pos, vel, c->rank, acc_sel(c), c->pm);
+  if (c->p2p_on) {
+    KDNB_LAUNCH(c, zero_acc_kernel, 1184, 256, 0, acc_sel(c), 3ull * c->n);
+  } else {
+    KDNB_CUDA_TRY(c, cudaMemsetAsync(c->acc_t, 0, 3ull * c->n * sizeof(double), c->stream));
+  }
   KDNB_CHECK_LAUNCH(c);
-  // a[k] = 0 (:659-661)
-  KDNB_CUDA_TRY(c, cudaMemsetAsync(c->acc_t, 0, 3ull * c->n * sizeof(double), c->stream));
   c->tree_valid = false;  // positions moved: the tree no longer describes them
   return 0;
 }
@@ -97,21 +126,23 @@ int soa_to_aos(Ctx* c) {
   return 0;
 }
 
-__global__ void __launch_bounds__(256) gather_acc_kernel(uint32_t n, const uint32_t* __restrict__ rank,
-                                                         const double* __restrict__ acc_t, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) gather_acc_kernel(uint32_t n, const uint32_t* __restrict__ rank, AccSel sel,
+                                                         double* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t j = rank[i];
+  const double* acc_t = acc_buf(sel);
   out[3ull * i + 0] = acc_t[3 * j + 0];
   out[3ull * i + 1] = acc_t[3 * j + 1];
   out[3ull * i + 2] = acc_t[3 * j + 2];
 }
 
 __global__ void __launch_bounds__(256) scatter_acc_kernel(uint32_t n, const uint32_t* __restrict__ rank,
-                                                          const double* __restrict__ in, double* __restrict__ acc_t) {
+                                                          const double* __restrict__ in, AccSel sel) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t j = rank[i];
+  double* acc_t = acc_buf(sel);
   acc_t[3 * j + 0] = in[3ull * i + 0];
   acc_t[3 * j + 1] = in[3ull * i + 1];
   acc_t[3 * j + 2] = in[3ull * i + 2];
@@ -129,14 +160,14 @@ __global__ void __launch_bounds__(256) gather_counts_kernel(uint32_t n, const ui
 
 int gather_acc(Ctx* c, double* dst) {
   const uint32_t n = (uint32_t)c->n;
-  KDNB_LAUNCH(c, gather_acc_kernel, (n + 255) / 256, 256, 0, n, c->rank, c->acc_t, dst);
+  KDNB_LAUNCH(c, gather_acc_kernel, (n + 255) / 256, 256, 0, n, c->rank, acc_sel(c), dst);
   KDNB_CHECK_LAUNCH(c);
   return 0;
 }
 
 int scatter_acc(Ctx* c, const double* src) {
   const uint32_t n = (uint32_t)c->n;
-  KDNB_LAUNCH(c, scatter_acc_kernel, (n + 255) / 256, 256, 0, n, c->rank, src, c->acc_t);
+  KDNB_LAUNCH(c, scatter_acc_kernel, (n + 255) / 256, 256, 0, n, c->rank, src, acc_sel(c));
   KDNB_CHECK_LAUNCH(c);
   return 0;
 }

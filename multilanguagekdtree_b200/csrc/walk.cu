@@ -186,7 +186,8 @@ enum : int { K_NONE = 0, K_FAR = 1, K_NEAR = 2, K_SERIAL = 3 };
 template <int PPL, int MINB, bool EXACT, bool COUNTS>
 __global__ void __launch_bounds__(WALK_THREADS, MINB)
 walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, double* __restrict__ acc_t,
-            uint32_t slot_begin, uint32_t slot_end, double theta2, unsigned long long* __restrict__ wcounts) {
+            uint32_t slot_begin, uint32_t slot_end, double theta2, unsigned long long* __restrict__ wcounts,
+            P2P p2p) {
   __shared__ WalkSmem<PPL> S;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
@@ -217,7 +218,7 @@ walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, doub
     cv[u] = ca[u] = cl[u] = cp[u] = 0;
     ln[u] = 0;
   }
-  if (base >= slot_end) return;
+  const bool warp_has_work = base < slot_end;  // no early exit: every warp joins the end-of-kernel handshake below
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     lo[k] = warp_min(lo[k]);
@@ -227,7 +228,7 @@ walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, doub
   __syncwarp();
   const double far_margin = 1.0 - 1e-9, near_margin = 1.0 + 1e-9;
 
-  int sp = 1;
+  int sp = warp_has_work ? 1 : 0;
   while (sp > 0) {
     // ---- pop a batch: lane l takes entry sp+l after the pop (order inside a batch is irrelevant)
     const int room = WALK_STACK - sp;
@@ -398,13 +399,32 @@ walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, doub
     }
     __syncwarp();
   }
+  // ---- results.  Single GPU / NCCL mode: tree-ordered accelerations into the local acc_t.  Peer mode: the same
+  // 24 bytes go straight into EVERY rank's acc_t over NVLink (this rank's shard of everyone's copy), followed by a
+  // system-scope fence; the last CTA to finish then raises this rank's flag on every peer (p2p_wait_kernel consumes it).
+  const bool peer = p2p.world > 1;
+  uint32_t epoch = 0;
+  uint64_t boff = 0;
+  if (peer) {
+    epoch = *p2p.epoch;
+    boff = (uint64_t)(epoch & 1u) * p2p.stride;
+  }
 #pragma unroll
   for (int u = 0; u < PPL; ++u) {
     drain_list<EXACT, COUNTS>(S.lpos[w][u], S.lmask[w][u], ln[u], lane, px[u], py[u], pz[u], ax[u], ay[u], az[u], cp[u]);
     if (slot[u] < slot_end) {
-      acc_t[3ull * slot[u] + 0] = ax[u];
-      acc_t[3ull * slot[u] + 1] = ay[u];
-      acc_t[3ull * slot[u] + 2] = az[u];
+      if (!peer) {
+        acc_t[3ull * slot[u] + 0] = ax[u];
+        acc_t[3ull * slot[u] + 1] = ay[u];
+        acc_t[3ull * slot[u] + 2] = az[u];
+      } else {
+        for (int r = 0; r < p2p.world; ++r) {
+          double* dst = p2p.acc[r] + boff + 3ull * slot[u];
+          dst[0] = ax[u];
+          dst[1] = ay[u];
+          dst[2] = az[u];
+        }
+      }
       if (COUNTS) {
         wcounts[4ull * slot[u] + 0] = cv[u];
         wcounts[4ull * slot[u] + 1] = ca[u];
@@ -413,6 +433,42 @@ walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, doub
       }
     }
   }
+  if (peer) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t done = atomicAdd(p2p.cta_done, 1u);
+      if (done == gridDim.x - 1) {
+        *p2p.cta_done = 0;
+        __threadfence_system();
+        for (int r = 0; r < p2p.world; ++r) *reinterpret_cast<volatile uint32_t*>(p2p.flags[r] + p2p.rank) = epoch + 1u;
+      }
+    }
+  }
+}
+
+// one CTA per GPU: wait until every rank (this one included) has published the accelerations of the current step
+__global__ void p2p_wait_kernel(uint32_t* state, int world) {
+  const uint32_t target = state[0] + 1u;
+  volatile uint32_t* flags = state + 4;
+  if ((int)threadIdx.x < world) {
+    const long long t0 = clock64();
+    while (flags[threadIdx.x] < target) {
+      if (clock64() - t0 > (30LL << 30)) {  // ~15 s: a peer died; record it instead of hanging for ever
+        state[2] = 1u;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  if (threadIdx.x == 0) state[0] = target;
+}
+
+int p2p_wait_step(Ctx* c) {
+  KDNB_LAUNCH(c, p2p_wait_kernel, 1, 32, 0, c->p2p_state, c->world);
+  KDNB_CHECK_LAUNCH(c);
+  return 0;
 }
 
 template <int PPL, int MINB>
@@ -421,7 +477,9 @@ static void launch_walk(Ctx* c, uint32_t begin, uint32_t end) {
   const uint32_t grid = (groups + WALK_WARPS - 1) / WALK_WARPS;
   const bool counts = (c->flags & KDNB_FLAG_WALK_COUNTS) != 0;
   const bool exact = (c->flags & KDNB_FLAG_EXACT_MATH) != 0;
-#define KDNB_WALK_ARGS c->nodes, c->posm, c->acc_t, begin, end, c->theta2, c->wcounts
+  P2P pp = c->p2p;
+  if (!c->p2p_on) pp.world = 0;
+#define KDNB_WALK_ARGS c->nodes, c->posm, c->acc_t, begin, end, c->theta2, c->wcounts, pp
   if (exact && counts)
     KDNB_LAUNCH(c, (walk_kernel<PPL, 1, true, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
   else if (exact)
