@@ -389,3 +389,19 @@ def test_graph_replay_equals_plain_launches(orc):
         a.simple_sim(1e-3, 5)            # graph reused
         b.simple_sim(1e-3, 2); b.simple_sim(1e-3, 2); b.simple_sim(1e-3, 1)
         assert a.download().tobytes() == b.download().tobytes()
+
+
+def test_kdtree_sim_cli(orc):
+    """The C++ driver mirrors Parallel/RustVersion/src/main.rs: --number/-n required, --steps/-s default 1, prints seconds."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(__file__)), "multilanguagekdtree_b200", "kdtree-sim")
+    if not os.path.exists(exe):
+        pytest.skip("kdtree-sim not built")
+    r = subprocess.run([exe, "--number", "20000", "--steps", "3"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert float(r.stdout.strip()) > 0.0
+    r = subprocess.run([exe, "-n", "500", "-s", "2", "--verbose"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "walk=" in r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=30)
+    assert r.returncode == 2 and "--number" in r.stderr
