@@ -30,6 +30,7 @@ struct Pos3c {
 // ------------------------------------------------------------------------------------------ global levels
 
 __global__ void build_root(uint32_t* tstart, uint32_t* tlen, uint32_t* tnode, uint32_t n) {
+  pdl_sync();
   tstart[0] = 0;
   tlen[0] = n;
   tnode[0] = 0;
@@ -108,6 +109,7 @@ level_count(Pos3c pos, Lists L, int level, uint32_t cps, uint32_t mp, int layout
             uint32_t* __restrict__ tlen, uint32_t* __restrict__ tnode, uint32_t* __restrict__ tmid,
             uint8_t* __restrict__ tsd, WNode* __restrict__ nodes, const uint32_t* __restrict__ rk, uint32_t n,
             uint32_t* __restrict__ tmr, uint32_t* __restrict__ cnt, const uint32_t* __restrict__ flat) {
+  pdl_sync();
   __shared__ uint32_t wsum[LVL_THREADS / 32];
   __shared__ SegStats st;
   const uint32_t seg = blockIdx.x / cps, chunk = blockIdx.x % cps, e = blockIdx.y;
@@ -148,6 +150,7 @@ __global__ void __launch_bounds__(LVL_THREADS) level_scatter(Lists Lin, Lists Lo
                                                              const uint32_t* __restrict__ tmr,
                                                              const uint32_t* __restrict__ cnt,
                                                              const uint32_t* __restrict__ flat) {
+  pdl_sync();
   constexpr int IPT = LVL_CHUNK / LVL_THREADS;  // 8
   __shared__ uint32_t wtot[LVL_THREADS / 32];
   const uint32_t seg = blockIdx.x / cps, chunk = blockIdx.x % cps, e = blockIdx.y;
@@ -247,6 +250,7 @@ build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_
              const uint32_t* __restrict__ tnode, uint32_t* __restrict__ inv, WNode* __restrict__ nodes,
              double4* __restrict__ ms, uint32_t* __restrict__ perm, uint32_t* __restrict__ rank,
              PosM* __restrict__ posm, const uint32_t* __restrict__ flat) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BotSmem& S = *reinterpret_cast<BotSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -491,6 +495,7 @@ build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_
 // m / cm for the global levels (single CTA; at most a few thousand nodes)
 __global__ void __launch_bounds__(1024) build_topup(int l0, const uint32_t* __restrict__ tnode,
                                                     WNode* __restrict__ nodes, double4* __restrict__ ms) {
+  pdl_sync();
   for (int lev = l0 - 1; lev >= 0; --lev) {
     const uint32_t nn = 1u << lev, off = nn - 1;
     for (uint32_t s = threadIdx.x; s < nn; s += blockDim.x) {
@@ -511,6 +516,7 @@ __global__ void __launch_bounds__(1024) build_topup(int l0, const uint32_t* __re
 // ------------------------------------------------------------------------------------------ host side
 
 __global__ void fill_unused(WNode* nodes, uint64_t count) {
+  pdl_sync();
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) {
     WNode nd;
@@ -563,6 +569,7 @@ int build_tree(Ctx* c) {
 
 // ---- expand device nodes to the C-ABI record (kdnb_node), the mirror of `enum KDTree` (array_kd_tree.rs:18-34)
 __global__ void export_nodes(const WNode* __restrict__ nodes, uint64_t count, kdnb_node* __restrict__ out) {
+  pdl_sync();
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const WNode nd = nodes[i];

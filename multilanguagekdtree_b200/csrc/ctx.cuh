@@ -1,6 +1,7 @@
 // ctx.cuh — the context behind the opaque kdnb_ctx handle: device buffers, level plan, stream, counters.
 #pragma once
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -86,6 +87,7 @@ struct Ctx {
   int rank_id = 0, world = 1;
   void* nccl_comm = nullptr;
   uint64_t shard_slots = 0;  // tree slots per rank (multiple of 32)
+  bool use_pdl = false;      // programmatic dependent launch between the kernels of a step (opt-in: KDNB_PDL=1)
   bool p2p_ready = false;    // peer set-up attempted for the current allocation
   bool p2p_on = false;       // accelerations exchanged by peer stores inside the walk kernel (else ncclAllGather)
   P2P p2p = {};
@@ -132,11 +134,34 @@ int gather_counts(Ctx* c, unsigned long long* dst_orig_order);
 // peak.cu
 int measure_fp64_peak(Ctx* c, double* tflops);
 
-#define KDNB_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
-  do {                                                                           \
-    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);             \
-    (ctx)->launches++;                                                           \
-  } while (0)
+// Programmatic dependent launch (opt-in, KDNB_PDL=1): every kernel of the step can be launched with the
+// programmatic-stream-serialization attribute and starts with pdl_sync() — it signals that ITS successor may be scheduled (the successor's launch and
+// prologue then overlap this kernel's tail) and waits until its PREDECESSOR has completed and flushed its writes.
+// The step is a chain of ~50 kernels of 5-35 us at N=1M, so the launch gaps are a visible share of the build.
+__device__ __forceinline__ void pdl_sync() {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+template <typename... KArgs, typename... Args>
+inline void kdnb_launch(Ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = c->use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+  c->launches++;
+}
+
+#define KDNB_LAUNCH(ctx, kernel, grid, block, smem, ...) kdnb_launch((ctx), kernel, dim3(grid), dim3(block), (smem), __VA_ARGS__)
 
 #define KDNB_CHECK_LAUNCH(ctx)                                                   \
   do {                                                                           \

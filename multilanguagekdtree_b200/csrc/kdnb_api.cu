@@ -393,6 +393,7 @@ kdnb_ctx* kdnb_create(const kdnb_config* cfg) {
     return nullptr;
   }
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
+  c->use_pdl = getenv("KDNB_PDL") != nullptr;  // measured: no gain on top of CUDA-graph replay (profiles/README.md)
   return h;
 }
 

@@ -32,6 +32,7 @@ static AccSel acc_sel(const Ctx* c) {
 __global__ void __launch_bounds__(256) kick_drift_kernel(uint32_t n, double dt, V3 pos, V3 vel,
                                                          const uint32_t* __restrict__ rank, AccSel sel,
                                                          PosM* __restrict__ pm) {
+  pdl_sync();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t j = rank[i];
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(256) kick_drift_kernel(uint32_t n, double dt, 
 
 // a[k] = 0 (:659-661), coalesced over the buffer the kick just consumed
 __global__ void __launch_bounds__(256) zero_acc_kernel(AccSel sel, uint64_t count) {
+  pdl_sync();
   double* acc_t = acc_buf(sel);
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
     acc_t[i] = 0.0;
@@ -78,6 +80,7 @@ int kick_drift(Ctx* c, double dt) {
 __global__ void __launch_bounds__(256) aos_to_soa_kernel(uint32_t n, const kdnb_particle* __restrict__ aos, V3 pos,
                                                          V3 vel, double* __restrict__ radius,
                                                          double* __restrict__ mass, PosM* __restrict__ pm) {
+  pdl_sync();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double2* q = reinterpret_cast<const double2*>(aos + i);
@@ -101,6 +104,7 @@ __global__ void __launch_bounds__(256) aos_to_soa_kernel(uint32_t n, const kdnb_
 __global__ void __launch_bounds__(256) soa_to_aos_kernel(uint32_t n, kdnb_particle* __restrict__ aos, V3 pos, V3 vel,
                                                          const double* __restrict__ radius,
                                                          const double* __restrict__ mass) {
+  pdl_sync();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double2* q = reinterpret_cast<double2*>(aos + i);
@@ -128,6 +132,7 @@ int soa_to_aos(Ctx* c) {
 
 __global__ void __launch_bounds__(256) gather_acc_kernel(uint32_t n, const uint32_t* __restrict__ rank, AccSel sel,
                                                          double* __restrict__ out) {
+  pdl_sync();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t j = rank[i];
@@ -139,6 +144,7 @@ __global__ void __launch_bounds__(256) gather_acc_kernel(uint32_t n, const uint3
 
 __global__ void __launch_bounds__(256) scatter_acc_kernel(uint32_t n, const uint32_t* __restrict__ rank,
                                                           const double* __restrict__ in, AccSel sel) {
+  pdl_sync();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t j = rank[i];
@@ -151,6 +157,7 @@ __global__ void __launch_bounds__(256) scatter_acc_kernel(uint32_t n, const uint
 __global__ void __launch_bounds__(256) gather_counts_kernel(uint32_t n, const uint32_t* __restrict__ rank,
                                                             const unsigned long long* __restrict__ in,
                                                             unsigned long long* __restrict__ out) {
+  pdl_sync();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t j = rank[i];

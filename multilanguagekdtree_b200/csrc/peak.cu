@@ -5,6 +5,7 @@
 namespace kdnb {
 
 __global__ void __launch_bounds__(256) dfma_chain(double* out, int iters, double a, double b) {
+  pdl_sync();
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
   for (int i = 0; i < iters; ++i) {
 #pragma unroll

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_upsweep(Pos3 pos, const uin
                                                              uint32_t n, int shift, uint32_t ntiles,
                                                              uint32_t* __restrict__ hist,
                                                              const uint32_t* __restrict__ flat) {
+  pdl_sync();
   __shared__ uint32_t h[256];
   const int d = blockIdx.y;
   if (flat[d]) return;  // all coordinates of this dimension are equal: its list is never consulted (build.cu)
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_upsweep(Pos3 pos, const uin
 __global__ void __launch_bounds__(256) sort_scan_rows(uint32_t* __restrict__ hist, uint32_t ntiles,
                                                       uint32_t* __restrict__ tot,
                                                       const uint32_t* __restrict__ flat) {
+  pdl_sync();
   __shared__ uint32_t wsum[8];
   if (flat[blockIdx.y]) return;
   uint32_t* row = hist + ((uint64_t)blockIdx.y * 256 + blockIdx.x) * ntiles;
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const u
                                                                const uint32_t* __restrict__ hist,
                                                                const uint32_t* __restrict__ tot,
                                                                const uint32_t* __restrict__ flat) {
+  pdl_sync();
   __shared__ uint32_t wcnt[SORT_THREADS / 32][256];
   __shared__ uint32_t base[256];
   __shared__ uint32_t toff[256];
@@ -196,9 +199,11 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const u
 // keeps the lower dimension on ties) and its sorted list is never consulted: sorting and partitioning it is skipped.
 // Dimension 0 is always kept — it is the tie winner when all extents are 0 and it orders the leaves.
 __global__ void flat_init(uint32_t* flat) {
+  pdl_sync();
   if (threadIdx.x < 3) flat[threadIdx.x] = threadIdx.x > 0 ? 1u : 0u;
 }
 __global__ void __launch_bounds__(256) flat_detect(Pos3 pos, uint32_t n, uint32_t* __restrict__ flat) {
+  pdl_sync();
   const int d = blockIdx.y + 1;
   const uint64_t k0 = f64_key(pos.p[d][0]);
   bool differs = false;
@@ -210,6 +215,7 @@ __global__ void __launch_bounds__(256) flat_detect(Pos3 pos, uint32_t n, uint32_
 // rk[d][id] = rank of particle id in the sorted list of dimension d (read by the global partition levels, build.cu)
 __global__ void __launch_bounds__(256) rank_from_lists(const uint32_t* __restrict__ lists, uint32_t n,
                                                        uint32_t* __restrict__ rk, const uint32_t* __restrict__ flat) {
+  pdl_sync();
   const int d = blockIdx.y;
   if (flat[d]) return;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -183,11 +183,12 @@ __device__ __forceinline__ double warp_max(double v) {
 
 enum : int { K_NONE = 0, K_FAR = 1, K_NEAR = 2, K_SERIAL = 3 };
 
-template <int PPL, int MINB, bool EXACT, bool COUNTS>
+template <int PPL, int MINB, bool EXACT, bool COUNTS, bool PEER>
 __global__ void __launch_bounds__(WALK_THREADS, MINB)
 walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, double* __restrict__ acc_t,
             uint32_t slot_begin, uint32_t slot_end, double theta2, unsigned long long* __restrict__ wcounts,
             P2P p2p) {
+  pdl_sync();
   __shared__ WalkSmem<PPL> S;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
@@ -218,7 +219,8 @@ walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, doub
     cv[u] = ca[u] = cl[u] = cp[u] = 0;
     ln[u] = 0;
   }
-  const bool warp_has_work = base < slot_end;  // no early exit: every warp joins the end-of-kernel handshake below
+  const bool warp_has_work = base < slot_end;
+  if (!PEER && !warp_has_work) return;  // (peer mode: no early exit, every warp joins the end-of-kernel handshake)
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     lo[k] = warp_min(lo[k]);
@@ -402,7 +404,7 @@ walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, doub
   // ---- results.  Single GPU / NCCL mode: tree-ordered accelerations into the local acc_t.  Peer mode: the same
   // 24 bytes go straight into EVERY rank's acc_t over NVLink (this rank's shard of everyone's copy), followed by a
   // system-scope fence; the last CTA to finish then raises this rank's flag on every peer (p2p_wait_kernel consumes it).
-  const bool peer = p2p.world > 1;
+  const bool peer = PEER && p2p.world > 1;
   uint32_t epoch = 0;
   uint64_t boff = 0;
   if (peer) {
@@ -433,7 +435,7 @@ walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, doub
       }
     }
   }
-  if (peer) {
+  if (PEER && peer) {
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -449,6 +451,7 @@ walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, doub
 
 // one CTA per GPU: wait until every rank (this one included) has published the accelerations of the current step
 __global__ void p2p_wait_kernel(uint32_t* state, int world) {
+  pdl_sync();
   const uint32_t target = state[0] + 1u;
   volatile uint32_t* flags = state + 4;
   if ((int)threadIdx.x < world) {
@@ -480,14 +483,17 @@ static void launch_walk(Ctx* c, uint32_t begin, uint32_t end) {
   P2P pp = c->p2p;
   if (!c->p2p_on) pp.world = 0;
 #define KDNB_WALK_ARGS c->nodes, c->posm, c->acc_t, begin, end, c->theta2, c->wcounts, pp
+  const bool peer = pp.world > 1;
   if (exact && counts)
-    KDNB_LAUNCH(c, (walk_kernel<PPL, 1, true, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
+    KDNB_LAUNCH(c, (walk_kernel<PPL, 1, true, true, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
   else if (exact)
-    KDNB_LAUNCH(c, (walk_kernel<PPL, 1, true, false>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
+    KDNB_LAUNCH(c, (walk_kernel<PPL, 1, true, false, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
   else if (counts)
-    KDNB_LAUNCH(c, (walk_kernel<PPL, 1, false, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
+    KDNB_LAUNCH(c, (walk_kernel<PPL, 1, false, true, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
+  else if (peer)
+    KDNB_LAUNCH(c, (walk_kernel<PPL, MINB, false, false, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
   else
-    KDNB_LAUNCH(c, (walk_kernel<PPL, MINB, false, false>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
+    KDNB_LAUNCH(c, (walk_kernel<PPL, MINB, false, false, false>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
 #undef KDNB_WALK_ARGS
 }
 
