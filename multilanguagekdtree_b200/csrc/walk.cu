@@ -30,8 +30,6 @@
 
 namespace kdnb {
 
-constexpr int WALK_THREADS = 64;
-constexpr int WALK_WARPS = WALK_THREADS / 32;
 constexpr int WALK_STACK = 320;  // soft capacity: batches shrink as the stack fills (see nb below)
 constexpr int WALK_SLACK = 32;   // depth-first tail when the stack is at capacity (tree depth <= 27 at 1e8 particles)
 constexpr int WALK_LIST = 64;    // interaction-list capacity per 32 particles (>= 32 + largest MAX_PARTS)
@@ -54,7 +52,7 @@ __device__ __forceinline__ double neg_m_over_r3_fast(double mneg, double d2) {
   return fma(__dmul_rn(mq, e), q, mq);
 }
 
-template <int PPL>
+template <int PPL, int WALK_WARPS>
 struct WalkSmem {
   uint32_t snode[WALK_WARPS][WALK_STACK + WALK_SLACK];
   uint32_t smask[WALK_WARPS][PPL][WALK_STACK + WALK_SLACK];
@@ -183,13 +181,14 @@ __device__ __forceinline__ double warp_max(double v) {
 
 enum : int { K_NONE = 0, K_FAR = 1, K_NEAR = 2, K_SERIAL = 3 };
 
-template <int PPL, int MINB, bool EXACT, bool COUNTS, bool PEER>
+template <int PPL, int WALK_THREADS, int MINB, bool EXACT, bool COUNTS, bool PEER>
 __global__ void __launch_bounds__(WALK_THREADS, MINB)
 walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, double* __restrict__ acc_t,
             uint32_t slot_begin, uint32_t slot_end, double theta2, unsigned long long* __restrict__ wcounts,
             P2P p2p) {
   pdl_sync();
-  __shared__ WalkSmem<PPL> S;
+  constexpr int WALK_WARPS = WALK_THREADS / 32;
+  __shared__ WalkSmem<PPL, WALK_WARPS> S;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
   const uint32_t base = slot_begin + (blockIdx.x * WALK_WARPS + w) * (32 * PPL);
@@ -474,8 +473,9 @@ int p2p_wait_step(Ctx* c) {
   return 0;
 }
 
-template <int PPL, int MINB>
+template <int PPL, int MINB, int WALK_THREADS = 64>
 static void launch_walk(Ctx* c, uint32_t begin, uint32_t end) {
+  constexpr int WALK_WARPS = WALK_THREADS / 32;
   const uint32_t groups = (end - begin + 32 * PPL - 1) / (32 * PPL);
   const uint32_t grid = (groups + WALK_WARPS - 1) / WALK_WARPS;
   const bool counts = (c->flags & KDNB_FLAG_WALK_COUNTS) != 0;
@@ -485,15 +485,15 @@ static void launch_walk(Ctx* c, uint32_t begin, uint32_t end) {
 #define KDNB_WALK_ARGS c->nodes, c->posm, c->acc_t, begin, end, c->theta2, c->wcounts, pp
   const bool peer = pp.world > 1;
   if (exact && counts)
-    KDNB_LAUNCH(c, (walk_kernel<PPL, 1, true, true, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
+    KDNB_LAUNCH(c, (walk_kernel<PPL, WALK_THREADS, 1, true, true, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
   else if (exact)
-    KDNB_LAUNCH(c, (walk_kernel<PPL, 1, true, false, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
+    KDNB_LAUNCH(c, (walk_kernel<PPL, WALK_THREADS, 1, true, false, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
   else if (counts)
-    KDNB_LAUNCH(c, (walk_kernel<PPL, 1, false, true, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
+    KDNB_LAUNCH(c, (walk_kernel<PPL, WALK_THREADS, 1, false, true, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
   else if (peer)
-    KDNB_LAUNCH(c, (walk_kernel<PPL, MINB, false, false, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
+    KDNB_LAUNCH(c, (walk_kernel<PPL, WALK_THREADS, MINB, false, false, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
   else
-    KDNB_LAUNCH(c, (walk_kernel<PPL, MINB, false, false, false>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
+    KDNB_LAUNCH(c, (walk_kernel<PPL, WALK_THREADS, MINB, false, false, false>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
 #undef KDNB_WALK_ARGS
 }
 
@@ -510,6 +510,12 @@ int walk(Ctx* c) {
       return s ? atoi(s) : 0;
     }();
     switch (cfg) {
+      case 3216: launch_walk<1, 16, 32>(c, begin, end); break;
+      case 3224: launch_walk<1, 24, 32>(c, begin, end); break;
+      case 3232: launch_walk<1, 32, 32>(c, begin, end); break;
+      case 12806: launch_walk<1, 6, 128>(c, begin, end); break;
+      case 12808: launch_walk<1, 8, 128>(c, begin, end); break;
+      case 25604: launch_walk<1, 4, 256>(c, begin, end); break;
       case 16: launch_walk<1, 6>(c, begin, end); break;
       case 110: launch_walk<1, 10>(c, begin, end); break;
       case 26: launch_walk<2, 6>(c, begin, end); break;
@@ -519,7 +525,7 @@ int walk(Ctx* c) {
       case 28: launch_walk<2, 8>(c, begin, end); break;
       case 210: launch_walk<2, 10>(c, begin, end); break;
       case 212: launch_walk<2, 12>(c, begin, end); break;
-      default: launch_walk<1, 12>(c, begin, end); break;
+      default: launch_walk<1, 32, 32>(c, begin, end); break;  // one warp per CTA, 32 CTAs per SM (64 registers)
     }
     KDNB_CHECK_LAUNCH(c);
   }
