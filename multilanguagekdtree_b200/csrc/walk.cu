@@ -86,7 +86,7 @@ __device__ __forceinline__ void interact(const Rec32& e, bool use, bool is_parti
 }
 
 // all lanes stream over one 32-particle list
-template <bool EXACT, bool COUNTS>
+template <bool EXACT, bool COUNTS, int DW>
 __device__ __forceinline__ void drain_list(const Rec32* __restrict__ lpos, const uint2* __restrict__ lmask, int cnt,
                                            int lane, double px, double py, double pz, double& ax, double& ay,
                                            double& az, unsigned long long& cp) {
@@ -104,7 +104,6 @@ __device__ __forceinline__ void drain_list(const Rec32* __restrict__ lpos, const
     // chains are interleaved by hand, stage by stage (left to the compiler they were emitted one after another and
     // the FP64 pipe idled on its own latency: profiles/README.md).  The list is padded to a multiple of DW with
     // masked-out entries.
-    constexpr int DW = 4;
     const uint32_t lanebit = 1u << lane;
     const int padded = (cnt + DW - 1) / DW * DW;
     if (lane < padded - cnt) {
@@ -118,9 +117,12 @@ __device__ __forceinline__ void drain_list(const Rec32* __restrict__ lpos, const
       double dx[DW], dy[DW], dz[DW], d2[DW], y[DW], y2[DW], ee[DW], mq[DW], q[DW];
       uint32_t use[DW];
       {  // the DW masks in two 16-byte loads ({mask, flag} pairs)
-        const uint4 m01 = *reinterpret_cast<const uint4*>(&lmask[i]);
-        const uint4 m23 = *reinterpret_cast<const uint4*>(&lmask[i + 2]);
-        use[0] = m01.x & lanebit, use[1] = m01.z & lanebit, use[2] = m23.x & lanebit, use[3] = m23.z & lanebit;
+#pragma unroll
+        for (int j = 0; j < DW; j += 2) {
+          const uint4 m = *reinterpret_cast<const uint4*>(&lmask[i + j]);
+          use[j] = m.x & lanebit;
+          use[j + 1] = m.z & lanebit;
+        }
       }
 #pragma unroll
       for (int j = 0; j < DW; ++j) {
@@ -181,7 +183,7 @@ __device__ __forceinline__ double warp_max(double v) {
 
 enum : int { K_NONE = 0, K_FAR = 1, K_NEAR = 2, K_SERIAL = 3 };
 
-template <int PPL, int WALK_THREADS, int MINB, bool EXACT, bool COUNTS, bool PEER>
+template <int PPL, int WALK_THREADS, int MINB, bool EXACT, bool COUNTS, bool PEER, int DW = 4>
 __global__ void __launch_bounds__(WALK_THREADS, MINB)
 walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, double* __restrict__ acc_t,
             uint32_t slot_begin, uint32_t slot_end, double theta2, unsigned long long* __restrict__ wcounts,
@@ -291,7 +293,7 @@ walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, doub
         const uint32_t bal = __ballot_sync(0xffffffffu, mine);
         const int add = __popc(bal);
         if (ln[u] + add > WALK_LIST) {
-          drain_list<EXACT, COUNTS>(S.lpos[w][u], S.lmask[w][u], ln[u], lane, px[u], py[u], pz[u], ax[u], ay[u], az[u], cp[u]);
+          drain_list<EXACT, COUNTS, DW>(S.lpos[w][u], S.lmask[w][u], ln[u], lane, px[u], py[u], pz[u], ax[u], ay[u], az[u], cp[u]);
           ln[u] = 0;
         }
         if (mine) {
@@ -342,7 +344,7 @@ walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, doub
         for (int u = 0; u < PPL; ++u) {
           if (ms[u] == 0) continue;
           if (ln[u] + cnt > WALK_LIST) {
-            drain_list<EXACT, COUNTS>(S.lpos[w][u], S.lmask[w][u], ln[u], lane, px[u], py[u], pz[u], ax[u], ay[u], az[u], cp[u]);
+            drain_list<EXACT, COUNTS, DW>(S.lpos[w][u], S.lmask[w][u], ln[u], lane, px[u], py[u], pz[u], ax[u], ay[u], az[u], cp[u]);
             ln[u] = 0;
           }
           if (lane < cnt) {
@@ -374,7 +376,7 @@ walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, doub
           open_any |= ms[u];
           if (am) {
             if (ln[u] + 1 > WALK_LIST) {
-              drain_list<EXACT, COUNTS>(S.lpos[w][u], S.lmask[w][u], ln[u], lane, px[u], py[u], pz[u], ax[u], ay[u], az[u], cp[u]);
+              drain_list<EXACT, COUNTS, DW>(S.lpos[w][u], S.lmask[w][u], ln[u], lane, px[u], py[u], pz[u], ax[u], ay[u], az[u], cp[u]);
               ln[u] = 0;
             }
             if (lane == 0) {
@@ -412,7 +414,7 @@ walk_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, doub
   }
 #pragma unroll
   for (int u = 0; u < PPL; ++u) {
-    drain_list<EXACT, COUNTS>(S.lpos[w][u], S.lmask[w][u], ln[u], lane, px[u], py[u], pz[u], ax[u], ay[u], az[u], cp[u]);
+    drain_list<EXACT, COUNTS, DW>(S.lpos[w][u], S.lmask[w][u], ln[u], lane, px[u], py[u], pz[u], ax[u], ay[u], az[u], cp[u]);
     if (slot[u] < slot_end) {
       if (!peer) {
         acc_t[3ull * slot[u] + 0] = ax[u];
@@ -473,7 +475,7 @@ int p2p_wait_step(Ctx* c) {
   return 0;
 }
 
-template <int PPL, int MINB, int WALK_THREADS = 64>
+template <int PPL, int MINB, int WALK_THREADS = 64, int DW = 4>
 static void launch_walk(Ctx* c, uint32_t begin, uint32_t end) {
   constexpr int WALK_WARPS = WALK_THREADS / 32;
   const uint32_t groups = (end - begin + 32 * PPL - 1) / (32 * PPL);
@@ -491,9 +493,9 @@ static void launch_walk(Ctx* c, uint32_t begin, uint32_t end) {
   else if (counts)
     KDNB_LAUNCH(c, (walk_kernel<PPL, WALK_THREADS, 1, false, true, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
   else if (peer)
-    KDNB_LAUNCH(c, (walk_kernel<PPL, WALK_THREADS, MINB, false, false, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
+    KDNB_LAUNCH(c, (walk_kernel<PPL, WALK_THREADS, MINB, false, false, true, DW>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
   else
-    KDNB_LAUNCH(c, (walk_kernel<PPL, WALK_THREADS, MINB, false, false, false>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
+    KDNB_LAUNCH(c, (walk_kernel<PPL, WALK_THREADS, MINB, false, false, false, DW>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
 #undef KDNB_WALK_ARGS
 }
 
@@ -510,6 +512,11 @@ int walk(Ctx* c) {
       return s ? atoi(s) : 0;
     }();
     switch (cfg) {
+      case 232: launch_walk<1, 32, 32, 2>(c, begin, end); break;
+      case 240: launch_walk<1, 40, 32, 2>(c, begin, end); break;
+      case 248: launch_walk<1, 48, 32, 2>(c, begin, end); break;
+      case 832: launch_walk<1, 32, 32, 8>(c, begin, end); break;
+      case 824: launch_walk<1, 24, 32, 8>(c, begin, end); break;
       case 3216: launch_walk<1, 16, 32>(c, begin, end); break;
       case 3224: launch_walk<1, 24, 32>(c, begin, end); break;
       case 3232: launch_walk<1, 32, 32>(c, begin, end); break;
