@@ -200,16 +200,22 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const u
 // Dimension 0 is always kept — it is the tie winner when all extents are 0 and it orders the leaves.
 __global__ void flat_init(uint32_t* flat) {
   pdl_sync();
-  if (threadIdx.x < 3) flat[threadIdx.x] = threadIdx.x > 0 ? 1u : 0u;
+  if (threadIdx.x < 4) flat[threadIdx.x] = threadIdx.x > 0 ? 1u : 0u;
 }
-__global__ void __launch_bounds__(256) flat_detect(Pos3 pos, uint32_t n, uint32_t* __restrict__ flat) {
+// flat[3] = 1 when, in addition, every z is +-0 and every mass is > 0: then every node's centre-of-mass z
+// (sum m*z / sum m) is +-0 as well, dz == 0 in every test and interaction, and the walk skips the z terms (walk2.cuh).
+__global__ void __launch_bounds__(256) flat_detect(Pos3 pos, const double* __restrict__ mass, uint32_t n,
+                                                   uint32_t* __restrict__ flat) {
   pdl_sync();
   const int d = blockIdx.y + 1;
   const uint64_t k0 = f64_key(pos.p[d][0]);
-  bool differs = false;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  bool differs = false, heavy = true;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     differs |= f64_key(pos.p[d][i]) != k0;
+    if (d == 2) heavy &= mass[i] > 0.0;
+  }
   if (differs) flat[d] = 0u;
+  if (d == 2 && (differs || !heavy || k0 != f64_key(0.0))) flat[3] = 0u;
 }
 
 // rk[d][id] = rank of particle id in the sorted list of dimension d (read by the global partition levels, build.cu)
@@ -229,7 +235,7 @@ int sort_lists(Ctx* c) {
   Pos3 pos = {{c->pos[0], c->pos[1], c->pos[2]}};
   dim3 gt(nt, 3), gs(256, 3);
   KDNB_LAUNCH(c, flat_init, 1, 32, 0, c->flat);
-  KDNB_LAUNCH(c, flat_detect, dim3(std::min<uint32_t>((n + 255) / 256, 1184u), 2), 256, 0, pos, n, c->flat);
+  KDNB_LAUNCH(c, flat_detect, dim3(std::min<uint32_t>((n + 255) / 256, 1184u), 2), 256, 0, pos, c->mass, n, c->flat);
   for (int pass = 0; pass < 8; ++pass) {
     const int shift = 8 * pass;
     const int src = (pass & 1) ? 1 : 0, dst = src ^ 1;  // pass 0 reads positions, writes buf1

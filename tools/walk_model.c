@@ -1,0 +1,215 @@
+// walk_model.c — development aid (NOT product, NOT test): replays the warp-level traversal schedule of
+// csrc/walk.cu on the CPU over the oracle's canonical tree and counts the events that set its instruction count
+// (pop batches and their fill, far / near / mixed / leaf nodes, deferred rounds, list entries and their mask
+// population).  Used to size queues and to predict the effect of schedule changes without GPU time.
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../oracle/kdtree_oracle.h"
+
+typedef struct {
+  double batches, popped, farn, nearn, mixed, leaves, entries, lanes, mixed_rounds, mixed_round_nodes, leaf_rounds,
+      leaf_round_nodes, max_sp, max_pend, drains, part_entries, tests, pack2, pack4, pack32, hist[33];
+} wm_stats;
+
+static inline int popc(uint32_t x) { return __builtin_popcount(x); }
+static int pack(const uint32_t* m, int n, int K) {
+  uint32_t occ[64]; int cnt[64]; int ns = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!m[i]) continue;
+    int j = 0;
+    for (; j < ns; ++j) if (!(occ[j] & m[i]) && cnt[j] < K) break;
+    if (j == ns) occ[ns] = 0, cnt[ns] = 0, ns++;
+    occ[j] |= m[i]; cnt[j]++;
+  }
+  return ns;
+}
+static void packstats(wm_stats* o, const uint32_t* m, int n, int rep) {
+  o->pack2 += rep * pack(m, n, 2); o->pack4 += rep * pack(m, n, 4); o->pack32 += rep * pack(m, n, 32);
+  for (int i = 0; i < n; ++i) if (m[i]) o->hist[popc(m[i])] += rep;
+}
+
+// group = 32 consecutive tree slots starting at base; slot -> particle id through idx[]
+void wm_run(const okd_node* nodes, const okd_particle* parts, const uint64_t* idx, uint64_t n, double theta,
+            uint64_t first_group, uint64_t n_groups, uint64_t stride, int defer, int hard, wm_stats* out) {
+  const double theta2 = theta * theta;
+  memset(out, 0, sizeof(*out));
+  enum { CAP = 4096 };
+  uint32_t* snode = malloc(sizeof(uint32_t) * CAP);
+  uint32_t* smask = malloc(sizeof(uint32_t) * CAP);
+  uint32_t pn[CAP], pm[CAP], ln_[CAP], lm[CAP];
+  for (uint64_t g = 0; g < n_groups; ++g) {
+    const uint64_t base = (first_group + g * stride) * 32;
+    if (base >= n) break;
+    double px[32], py[32], pz[32], lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    uint32_t m0 = 0;
+    for (int l = 0; l < 32; ++l) {
+      if (base + l >= n) continue;
+      const okd_particle* p = &parts[idx[base + l]];
+      px[l] = p->p[0], py[l] = p->p[1], pz[l] = p->p[2];
+      m0 |= 1u << l;
+      for (int k = 0; k < 3; ++k) {
+        lo[k] = fmin(lo[k], p->p[k]);
+        hi[k] = fmax(hi[k], p->p[k]);
+      }
+    }
+    int sp = 0, pend = 0, pleaf = 0, list = 0;
+    snode[sp] = 0, smask[sp] = m0, sp++;
+    for (;;) {
+      const int room = hard - sp - 2 * pend;
+      if (defer && (pend >= 32 || (pend > 0 && (room <= 0 || sp == 0)))) {
+        const int r = pend < 32 ? pend : 32;
+        out->mixed_rounds++;
+        out->mixed_round_nodes += r;
+        int adds = 0;
+        uint32_t ams[32];
+        for (int i = 0; i < r; ++i) {
+          const uint32_t nd = pn[pend - 1 - i], mk = pm[pend - 1 - i];
+          const okd_node* q = &nodes[nd];
+          uint32_t am = 0;
+          for (int l = 0; l < 32; ++l)
+            if ((mk >> l) & 1) {
+              const double dx = px[l] - q->u.in.cm[0], dy = py[l] - q->u.in.cm[1], dz = pz[l] - q->u.in.cm[2];
+              const double d2 = dx * dx + dy * dy + dz * dz;
+              if (q->u.in.size * q->u.in.size < theta2 * d2) am |= 1u << l;
+            }
+          out->tests += popc(mk);
+          ams[i] = am;
+          if (am) {
+            adds++;
+            out->entries++;
+            out->lanes += popc(am);
+          }
+          const uint32_t ms = mk & ~am;
+          if (ms) {
+            snode[sp] = (uint32_t)q->u.in.right, smask[sp] = ms, sp++;
+            snode[sp] = (uint32_t)q->u.in.left, smask[sp] = ms, sp++;
+          }
+        }
+        packstats(out, ams, r, 1);
+        pend -= r;
+        if (list + adds > 64) out->drains++, list = 0;
+        list += adds;
+        if (sp > out->max_sp) out->max_sp = sp;
+        continue;
+      }
+      if (defer && (pleaf >= 32 || (pleaf > 0 && sp == 0 && pend == 0))) {
+        const int r = pleaf < 32 ? pleaf : 32;
+        out->leaf_rounds++;
+        out->leaf_round_nodes += r;
+        for (int k = 0; k < 8; ++k) {
+          int adds = 0;
+          uint32_t lms[32];
+          for (int i = 0; i < r; ++i) {
+            lms[i] = 0;
+            const uint32_t nd = ln_[pleaf - 1 - i], mk = lm[pleaf - 1 - i];
+            const okd_node* q = &nodes[nd];
+            if ((uint64_t)k < q->u.leaf.num_parts) {
+              // owner lane removed
+              uint32_t m = mk;
+              const uint64_t pid = q->u.leaf.leaf_parts[k];
+              for (int l = 0; l < 32; ++l)
+                if (base + l < n && idx[base + l] == pid) m &= ~(1u << l);
+              adds++;
+              out->entries++;
+              out->part_entries++;
+              out->lanes += popc(m);
+              lms[i] = m;
+            }
+          }
+          packstats(out, lms, r, 1);
+          if (list + adds > 64) out->drains++, list = 0;
+          list += adds;
+        }
+        pleaf -= r;
+        continue;
+      }
+      if (sp == 0) break;
+      int nb = sp < 32 ? sp : 32;
+      const int rm = room > 1 ? room : 1;
+      if (nb > rm) nb = rm;
+      sp -= nb;
+      out->batches++;
+      out->popped += nb;
+      int adds = 0;
+      uint32_t newn[64], newm[64], fms[32];
+      int nn = 0;
+      for (int i = 0; i < nb; ++i) {
+        const uint32_t nd = snode[sp + i], mk = smask[sp + i];
+        const okd_node* q = &nodes[nd];
+        fms[i] = 0;
+        if (!q->is_internal) {
+          out->leaves++;
+          if (defer) {
+            ln_[pleaf] = nd, lm[pleaf] = mk, pleaf++;
+          } else {
+            for (uint64_t k = 0; k < q->u.leaf.num_parts; ++k) {
+              uint32_t m = mk;
+              const uint64_t pid = q->u.leaf.leaf_parts[k];
+              for (int l = 0; l < 32; ++l)
+                if (base + l < n && idx[base + l] == pid) m &= ~(1u << l);
+              out->entries++, out->part_entries++;
+              out->lanes += popc(m);
+            }
+            if (list + (int)q->u.leaf.num_parts > 64) out->drains++, list = 0;
+            list += (int)q->u.leaf.num_parts;
+          }
+          continue;
+        }
+        double dmin2 = 0, dmax2 = 0;
+        for (int k = 0; k < 3; ++k) {
+          const double below = lo[k] - q->u.in.cm[k], above = q->u.in.cm[k] - hi[k];
+          const double dn = fmax(0.0, fmax(below, above)), df = fmax(fabs(below), fabs(above));
+          dmin2 += dn * dn, dmax2 += df * df;
+        }
+        const double size2 = q->u.in.size * q->u.in.size;
+        if (size2 < theta2 * dmin2 * (1 - 1e-9)) {
+          out->farn++;
+          fms[i] = mk;
+          adds++;
+          out->entries++;
+          out->lanes += popc(mk);
+        } else if (size2 >= theta2 * dmax2 * (1 + 1e-9)) {
+          out->nearn++;
+          newn[nn] = (uint32_t)q->u.in.right, newm[nn] = mk, nn++;
+          newn[nn] = (uint32_t)q->u.in.left, newm[nn] = mk, nn++;
+        } else {
+          out->mixed++;
+          if (defer) {
+            pn[pend] = nd, pm[pend] = mk, pend++;
+          } else {
+            uint32_t am = 0;
+            for (int l = 0; l < 32; ++l)
+              if ((mk >> l) & 1) {
+                const double dx = px[l] - q->u.in.cm[0], dy = py[l] - q->u.in.cm[1], dz = pz[l] - q->u.in.cm[2];
+                const double d2 = dx * dx + dy * dy + dz * dz;
+                if (size2 < theta2 * d2) am |= 1u << l;
+              }
+            if (am) {
+              out->entries++;
+              out->lanes += popc(am);
+              if (list + 1 > 64) out->drains++, list = 0;
+              list++;
+            }
+            const uint32_t ms = mk & ~am;
+            if (ms) {
+              newn[nn] = (uint32_t)q->u.in.right, newm[nn] = ms, nn++;
+              newn[nn] = (uint32_t)q->u.in.left, newm[nn] = ms, nn++;
+            }
+          }
+        }
+      }
+      if (defer) packstats(out, fms, nb, 1);
+      if (list + adds > 64) out->drains++, list = 0;
+      list += adds;
+      for (int i = 0; i < nn; ++i) snode[sp] = newn[i], smask[sp] = newm[i], sp++;
+      if (sp > out->max_sp) out->max_sp = sp;
+      if (pend > out->max_pend) out->max_pend = pend;
+    }
+  }
+  free(snode);
+  free(smask);
+}

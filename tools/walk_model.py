@@ -1,0 +1,29 @@
+"""Development aid: event counts of the walk schedule on the CPU (see walk_model.c).  Usage: python tools/walk_model.py [N] [groups]"""
+import ctypes as C, os, subprocess, sys
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from oracle import okd
+
+here = os.path.dirname(os.path.abspath(__file__))
+so = "/tmp/walk_model.so"
+subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(here, "walk_model.c"), "-lm"], check=True)
+lib = C.CDLL(so)
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+G = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
+o = okd.Oracle()
+parts = o.circular_orbits(N)
+nodes, idx, last = o.build_tree_canonical(parts, threads=8)
+n = len(parts)
+ngroups = (n + 31) // 32
+stride = max(1, ngroups // G)
+names = "batches popped far near mixed leaves entries lanes mixed_rounds mixed_round_nodes leaf_rounds leaf_round_nodes max_sp max_pend drains part_entries tests pack2 pack4 pack32".split() + [f"h{i}" for i in range(33)]
+for defer, hard in ((0, 320), (1, 320)):
+    st = (C.c_double * len(names))()
+    lib.wm_run(C.c_void_p(nodes.ctypes.data), C.c_void_p(parts.ctypes.data), C.c_void_p(idx.ctypes.data), C.c_uint64(n),
+               C.c_double(0.3), C.c_uint64(0), C.c_uint64(G), C.c_uint64(stride), C.c_int(defer), C.c_int(hard), st)
+    g = min(G, ngroups)
+    d = dict(zip(names, st))
+    print(f"defer={defer} hard={hard}: " + " ".join(f"{k}={v / g:.1f}" if not k.startswith('max') else f"{k}={v:.0f}" for k, v in zip(names, st) if not k.startswith('h')))
+    if defer: print("   hist popc:", " ".join(f"{int(d[f'h{i}']/g)}" for i in range(33)))
+    print(f"   lane efficiency {d['lanes'] / d['entries'] / 32:.3f}  batch fill {d['popped'] / d['batches']:.1f}"
+          + (f"  mixed round fill {d['mixed_round_nodes'] / max(1, d['mixed_rounds']):.1f} leaf round fill {d['leaf_round_nodes'] / max(1, d['leaf_rounds']):.1f}" if defer else ""))
