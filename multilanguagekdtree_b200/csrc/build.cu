@@ -230,7 +230,6 @@ static_assert(sizeof(BotTab) == 12, "BotTab");
 
 constexpr int BOT_THREADS = 512;
 constexpr int BOT_IPT = BOT_CAP / BOT_THREADS;  // 4
-constexpr int BOT_HEAP = 2048;
 constexpr int BOT_WARPS = BOT_THREADS / 32;
 
 struct BotSmem {
@@ -239,17 +238,27 @@ struct BotSmem {
   uint16_t segh[BOT_CAP];
   uint16_t scan[BOT_CAP];
   uint8_t side[BOT_CAP];
-  BotTab tab[BOT_HEAP];
   uint32_t wtot[BOT_WARPS];
   int flag;
+  BotTab tab[1];  // heap-indexed segment table, `heap` entries (dynamic shared memory; see bot_heap())
 };
 
-__global__ void __launch_bounds__(BOT_THREADS)
+// Heap size of the bottom kernel's segment table: a segment of <= BOT_CAP particles is split while it holds more than
+// mp, so the deepest local level is d = ceil(log2(BOT_CAP / mp)) and heap indices stay below 2^(d+1).  Sizing it to
+// MAX_PARTS (6 KB instead of 24 KB at mp = 8) lets four CTAs share an SM, so the 512 segments of N = 1M run as one wave.
+static inline uint32_t bot_heap(uint32_t mp) {
+  uint32_t d = 0;
+  while (((uint32_t)BOT_CAP >> d) > mp) ++d;
+  return 2u << d;
+}
+static inline size_t bot_smem_bytes(uint32_t mp) { return sizeof(BotSmem) + (bot_heap(mp) - 1) * sizeof(BotTab); }
+
+__global__ void __launch_bounds__(BOT_THREADS, 4)
 build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_t mp, int layout,
              const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ tlen,
              const uint32_t* __restrict__ tnode, uint32_t* __restrict__ inv, WNode* __restrict__ nodes,
              double4* __restrict__ ms, uint32_t* __restrict__ perm, uint32_t* __restrict__ rank,
-             PosM* __restrict__ posm, const uint32_t* __restrict__ flat) {
+             PosM* __restrict__ posm, const uint32_t* __restrict__ flat, uint32_t heap) {
   pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BotSmem& S = *reinterpret_cast<BotSmem*>(smem_raw);
@@ -293,12 +302,12 @@ build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_
     for (uint32_t h = nn + tid; h < 2 * nn; h += BOT_THREADS) {
       BotTab t = S.tab[h];
       if (t.kind == 2) {
-        if (2 * h + 1 < BOT_HEAP) S.tab[2 * h].kind = S.tab[2 * h + 1].kind = 2;
+        if (2 * h + 1 < heap) S.tab[2 * h].kind = S.tab[2 * h + 1].kind = 2;
         continue;
       }
       if (t.len <= mp) {
         S.tab[h].kind = 1;
-        if (2 * h + 1 < BOT_HEAP) S.tab[2 * h].kind = S.tab[2 * h + 1].kind = 2;
+        if (2 * h + 1 < heap) S.tab[2 * h].kind = S.tab[2 * h + 1].kind = 2;
         continue;
       }
       double mn[3], mx[3];
@@ -539,7 +548,7 @@ int build_tree(Ctx* c) {
   if (int rc = sort_lists(c)) return rc;
   if (!g_bottom_attr_set) {
     KDNB_CUDA_TRY(c, cudaFuncSetAttribute(build_bottom, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(BotSmem)));
+                                          (int)bot_smem_bytes(4)));
     g_bottom_attr_set = true;
   }
   Pos3c pos = {{c->pos[0], c->pos[1], c->pos[2]}};
@@ -558,8 +567,9 @@ int build_tree(Ctx* c) {
     cur ^= 1;
   }
   Lists Lb = {{c->list[cur], c->list[cur] + n, c->list[cur] + 2ull * n}};
-  KDNB_LAUNCH(c, build_bottom, 1u << c->l0, BOT_THREADS, sizeof(BotSmem), pos, c->pm, Lb, c->l0, c->mp,
-              c->layout, c->tstart, c->tlen, c->tnode, c->inv, c->nodes, c->ms, c->perm, c->rank, c->posm, c->flat);
+  KDNB_LAUNCH(c, build_bottom, 1u << c->l0, BOT_THREADS, bot_smem_bytes(c->mp), pos, c->pm, Lb, c->l0, c->mp,
+              c->layout, c->tstart, c->tlen, c->tnode, c->inv, c->nodes, c->ms, c->perm, c->rank, c->posm, c->flat,
+              bot_heap(c->mp));
   if (c->l0 > 0) KDNB_LAUNCH(c, build_topup, 1, 1024, 0, c->l0, c->tnode, c->nodes, c->ms);
   KDNB_CHECK_LAUNCH(c);
   c->tree_valid = true;

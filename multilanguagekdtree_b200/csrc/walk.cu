@@ -75,9 +75,16 @@ static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
   else if (counts)
     KDNB_LAUNCH(c, (walk2_kernel<false, true, true, 1>), grid, 32, 0, KDNB_WALK_ARGS);
   else if (peer)
-    KDNB_LAUNCH(c, (walk2_kernel<false, false, true, 32>), grid, 32, 0, KDNB_WALK_ARGS);
-  else
-    KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 32>), grid, 32, 0, KDNB_WALK_ARGS);
+    KDNB_LAUNCH(c, (walk2_kernel<false, false, true, 24>), grid, 32, 0, KDNB_WALK_ARGS);
+  else {
+    static const int minb = [] {
+      const char* s = getenv("KDNB_WALK_MINB");  // profiling knob: CTAs per SM the register budget is sized for
+      return s ? atoi(s) : 24;
+    }();
+    // 24 CTAs per SM = 80 registers: no spills, 1.4 % faster than 32 CTAs at 64 registers (profiles/README.md)
+    if (minb == 32) KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 32>), grid, 32, 0, KDNB_WALK_ARGS);
+    else KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 24>), grid, 32, 0, KDNB_WALK_ARGS);
+  }
 #undef KDNB_WALK_ARGS
 }
 

@@ -47,12 +47,16 @@ constexpr int W2_STACK = 320;  // soft capacity: batches shrink as the stack fil
 constexpr int W2_SLACK = 32;   // depth-first tail when the stack is at capacity (tree depth <= 27 at 1e8 particles)
 constexpr int W2_LIST = 64;    // interaction-list capacity (appends come in groups of <= 32)
 
+// 1.875 = the e^2 coefficient of (1 - e)^(-3/2); read from the constant bank as an instruction operand (as a literal
+// it costs two register moves per loop iteration at the 64-register budget)
+__constant__ double W2_C2 = 1.875;
+
 template <bool EXACT>
 struct W2Smem {
   uint32_t snode[W2_STACK + W2_SLACK];
   uint32_t smask[W2_STACK + W2_SLACK];
-  Rec32 lpos[W2_LIST];    // {x, y, z, m} of a monopole or of a leaf particle
-  uint32_t lmask[W2_LIST];
+  double lx[W2_LIST], ly[W2_LIST], lz[W2_LIST], lm[W2_LIST];  // monopoles / leaf particles, SoA: the drain loop reads
+  uint32_t lmask[W2_LIST];                                     // four consecutive interactions with 16-byte loads
   uint32_t lflag[EXACT ? W2_LIST : 4];  // 1 = leaf particle (the exact-math formulas differ, see interact<>)
   union {
     Rec32 mix[32];  // {cx, cy, cz, size^2} of the batch's mixed nodes, slot = owning lane
@@ -67,7 +71,8 @@ __device__ __forceinline__ void drain2(W2Smem<EXACT>& S, int cnt, int lane, doub
   __syncwarp();
   if (EXACT) {
     for (int i = 0; i < cnt; ++i) {
-      const Rec32 e = S.lpos[i];
+      Rec32 e;
+      e.a = S.lx[i], e.b = S.ly[i], e.c = S.lz[i], e.d = S.lm[i];
       const bool use = (S.lmask[i] >> lane) & 1u;
       interact<true>(e, use, S.lflag[i] != 0, px, py, pz, ax, ay, az);
     }
@@ -79,9 +84,7 @@ __device__ __forceinline__ void drain2(W2Smem<EXACT>& S, int cnt, int lane, doub
     const uint32_t lanebit = 1u << lane;
     const int padded = (cnt + DW - 1) / DW * DW;
     if (lane < padded - cnt) {
-      Rec32 z;
-      z.a = z.b = z.c = z.d = 0.0;
-      S.lpos[cnt + lane] = z;
+      S.lx[cnt + lane] = S.ly[cnt + lane] = S.lz[cnt + lane] = S.lm[cnt + lane] = 0.0;
       S.lmask[cnt + lane] = 0u;
     }
     __syncwarp();
@@ -90,12 +93,17 @@ __device__ __forceinline__ void drain2(W2Smem<EXACT>& S, int cnt, int lane, doub
       const uint4 m4 = *reinterpret_cast<const uint4*>(&S.lmask[i]);
       const uint32_t use[4] = {m4.x & lanebit, m4.y & lanebit, m4.z & lanebit, m4.w & lanebit};
 #pragma unroll
-      for (int j = 0; j < DW; ++j) {
-        const Rec32 e = S.lpos[i + j];
-        dx[j] = __dsub_rn(px, e.a);
-        dy[j] = __dsub_rn(py, e.b);
-        if (!FLATZ) dz[j] = __dsub_rn(pz, e.c);
-        mq[j] = -e.d;
+      for (int j = 0; j < DW; j += 2) {
+        const double2 ex = *reinterpret_cast<const double2*>(&S.lx[i + j]);
+        const double2 ey = *reinterpret_cast<const double2*>(&S.ly[i + j]);
+        const double2 em = *reinterpret_cast<const double2*>(&S.lm[i + j]);
+        dx[j] = __dsub_rn(px, ex.x), dx[j + 1] = __dsub_rn(px, ex.y);
+        dy[j] = __dsub_rn(py, ey.x), dy[j + 1] = __dsub_rn(py, ey.y);
+        if (!FLATZ) {
+          const double2 ez = *reinterpret_cast<const double2*>(&S.lz[i + j]);
+          dz[j] = __dsub_rn(pz, ez.x), dz[j + 1] = __dsub_rn(pz, ez.y);
+        }
+        mq[j] = -em.x, mq[j + 1] = -em.y;
       }
 #pragma unroll
       for (int j = 0; j < DW; ++j) d2[j] = __dmul_rn(dx[j], dx[j]);
@@ -107,7 +115,7 @@ __device__ __forceinline__ void drain2(W2Smem<EXACT>& S, int cnt, int lane, doub
       }
 #pragma unroll
       for (int j = 0; j < DW; ++j) {
-        double r;
+double r;
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d2[j]));
         y[j] = __hiloint2double(use[j] ? __double2hiint(r) : 0, 0);
       }
@@ -120,7 +128,7 @@ __device__ __forceinline__ void drain2(W2Smem<EXACT>& S, int cnt, int lane, doub
       }
 #pragma unroll
       for (int j = 0; j < DW; ++j) {
-        q[j] = fma(1.875, ee[j], 1.5);
+        q[j] = fma(W2_C2, ee[j], 1.5);
         mq[j] = __dmul_rn(mq[j], y[j]);  // -m * y0^3
       }
 #pragma unroll
@@ -278,7 +286,7 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __rest
         }
         if (mine) {
           const int i = ln + __popc(bal & lt);
-          S.lpos[i] = c;
+          S.lx[i] = c.a, S.ly[i] = c.b, S.lz[i] = c.c, S.lm[i] = c.d;
           S.lmask[i] = amask;
           if (EXACT) S.lflag[i] = 0u;
         }
@@ -323,9 +331,7 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __rest
         }
         if (valid) {
           const int i = ln + __popc(bal & lt);
-          Rec32 e;
-          e.a = qv.x, e.b = qv.y, e.c = qv.z, e.d = qv.m;
-          S.lpos[i] = e;
+          S.lx[i] = qv.x, S.ly[i] = qv.y, S.lz[i] = qv.z, S.lm[i] = qv.m;
           S.lmask[i] = m;
           if (EXACT) S.lflag[i] = 1u;
         }

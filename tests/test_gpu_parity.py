@@ -202,6 +202,58 @@ def test_walk_equal_mass_cube(orc, theta):
     assert rel_err(acc, oacc).max() <= 1e-11     # heavy cancellation in a uniform cube: |sum| << sum|terms|
 
 
+def _acc(parts, flags=0, mp=8, theta=0.3):
+    with kd.KDTreeSim(flags=flags, theta=theta, max_parts=mp) as sim:
+        sim.upload(parts)
+        sim.build_tree()
+        sim.calc_accel()
+        return sim.accel()
+
+
+def _fast_path_cases(orc):
+    ring = orc.circular_orbits(30000, seed=77)                       # planar, z == +0, masses > 0: z terms skipped
+    neg0 = ring.copy(); neg0["p"][::3, 2] = -0.0                      # -0.0 is still planar
+    lifted = ring.copy(); lifted["p"][:, 2] = 0.25                    # flat z list but cm_z != z exactly: general path
+    massless = ring.copy(); massless["m"][5] = 0.0                    # a zero mass disables the planar shortcut
+    return {"ring": ring, "neg0": neg0, "lifted": lifted, "massless": massless,
+            "cube": cube(20000, seed=4), "cube_unequal": cube(20000, seed=5, equal_mass=False)}
+
+
+@pytest.mark.parametrize("case", ["ring", "neg0", "lifted", "massless", "cube", "cube_unequal"])
+def test_walk_production_kernel_equals_counted_kernel(orc, case):
+    """The parity tests above run the counting variant of the walk kernel; the variant that simple_sim launches
+    (no counters, z terms skipped for planar inputs) must give the same accelerations BIT FOR BIT: same traversal,
+    same interaction lists, same operation order (a skipped z term is exactly +-0)."""
+    parts = _fast_path_cases(orc)[case]
+    fast = _acc(parts)
+    counted = _acc(parts, flags=kd.FLAG_WALK_COUNTS)
+    assert np.array_equal(fast, counted)        # value-exact (-0.0 == +0.0)
+    assert np.all(np.isfinite(fast))
+    if case in ("ring", "neg0"):
+        assert np.all(fast[:, 2] == 0.0)
+
+
+@pytest.mark.parametrize("mp", [4, 7])
+@pytest.mark.parametrize("shape", ["ring", "cube"])
+def test_walk_other_max_parts(orc, mp, shape):
+    parts = orc.circular_orbits(20000, seed=mp) if shape == "ring" else cube(12000, seed=mp)
+    acc, cnt, oacc, ocnt = _walk_case(orc, parts, mp=mp)
+    for k, f in enumerate(("node_visits", "accepts", "leaf_visits", "pp")):
+        assert np.array_equal(cnt[:, k], ocnt[f]), f
+    assert rel_err(acc, oacc).max() <= (ACC_RTOL if shape == "ring" else 1e-11)
+    assert np.array_equal(_acc(parts, mp=mp), acc)
+
+
+@pytest.mark.parametrize("mp", [16, 32])
+def test_walk_large_leaves(orc32, mp):
+    parts = orc32.circular_orbits(20000, seed=mp)
+    acc, cnt, oacc, ocnt = _walk_case(orc32, parts, mp=mp)
+    for k, f in enumerate(("node_visits", "accepts", "leaf_visits", "pp")):
+        assert np.array_equal(cnt[:, k], ocnt[f]), f
+    assert rel_err(acc, oacc).max() <= ACC_RTOL
+    assert np.array_equal(_acc(parts, mp=mp), acc)
+
+
 def test_walk_exact_math_flag(orc):
     parts = cube(8000, seed=2)
     acc, _, oacc, _ = _walk_case(orc, parts, flags=kd.FLAG_EXACT_MATH)

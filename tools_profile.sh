@@ -8,6 +8,6 @@ mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv \
     --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 --number $N --no-cpu \
     > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:walk_kernel -s 3 -c 1 -f -o gpurun_out/walk_${TAG} \
+ncu --set full --clock-control none --import-source on -k regex:walk2?_kernel -s 3 -c 1 -f -o gpurun_out/walk_${TAG} \
     python bench.py --steps 1 --warmup 3 --number $N --no-cpu > gpurun_out/ncu_walk_${TAG}.log 2>&1
 ls -la gpurun_out | tail -5
