@@ -59,7 +59,8 @@ struct Ctx {
   uint32_t* list[2] = {nullptr, nullptr};  // [3][n] per-dimension sorted id lists, ping-pong
   uint32_t* hist = nullptr;                // [3][256][ntiles]
   uint32_t* digit_tot = nullptr;           // [3][256]
-  uint32_t* flat = nullptr;                // [3] 1 = all coordinates of that dimension equal (lives behind digit_tot)
+  uint32_t* flat = nullptr;                // [3] 1 = all coordinates of that dimension equal (lives behind digit_tot); [3] planar walk
+  uint64_t* sort_state = nullptr;          // [16] key range, 32-bit key scaling, need64 flag (sort.cu)
   uint32_t* rk = nullptr;                  // [3][n] rank of every particle in the initial sorted list of each dimension
   uint32_t* tmr = nullptr;                 // level table: rk of the median element of every segment
   uint32_t* tstart = nullptr;              // level tables, level l at offset 2^l - 1

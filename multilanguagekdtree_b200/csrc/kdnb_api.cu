@@ -103,6 +103,7 @@ static void free_all(Ctx* c) {
   fr(c->list[1]);
   fr(c->hist);
   fr(c->digit_tot);
+  fr(c->sort_state);
   fr(c->rk);
   fr(c->tmr);
   fr(c->pm);
@@ -261,6 +262,7 @@ static int plan(Ctx* c, uint64_t n) {
     if (!rc) rc = dev_alloc(c, &c->hist, 3ull * 256 * c->ntiles);
     if (!rc) rc = dev_alloc(c, &c->digit_tot, 3 * 256 + 4);
     if (!rc) c->flat = c->digit_tot + 3 * 256;
+    if (!rc) rc = dev_alloc(c, &c->sort_state, 16);
     if (!rc) rc = dev_alloc(c, &c->rk, 3 * n);
     if (!rc) rc = dev_alloc(c, &c->tmr, table);
     if (!rc) rc = dev_alloc(c, &c->pm, n);

@@ -1,13 +1,24 @@
-// sort.cu — per-dimension sorted id lists: a hand-written stable LSD radix sort (8 passes x 8 bits) of the
-// order-preserving 64-bit keys of the x, y and z coordinates, all three dimensions batched in one launch
-// (blockIdx.y = dimension).  Starting from ids 0..n-1 and being stable, equal coordinates stay in ascending
-// particle-id order: the canonical tie-break of the build (SURVEY.md §7 hard part 1).
+// sort.cu — per-dimension sorted id lists: a hand-written stable LSD radix sort of the x, y and z coordinates, all
+// three dimensions batched in one launch (blockIdx.y = dimension).  Starting from ids 0..n-1 and being stable, equal
+// coordinates stay in ascending particle-id order: the canonical tie-break of the build (SURVEY.md §7 hard part 1).
+//
+// Two key widths share the kernels:
+//  * 32-bit (4 passes x 8 bits, the path that normally runs): key32 = trunc((x - min) * (2^32 - 1) / (max - min)), a
+//    MONOTONE (non-strict) map of the coordinate, so sorting by key32 orders everything except particles that share a
+//    key32.  sort_fixup then orders every run of equal key32 by the full 64-bit key (runs of <= 32 entries, one thread
+//    each; at N = 1M uniform over the extent a few hundred pairs collide) and checks every adjacent pair of longer runs;
+//    a longer run that is out of order raises need64.
+//  * 64-bit (8 passes x 8 bits over the order-preserving image of the f64): always correct; its 24 launches are
+//    gated on need64 and return at once when the 32-bit result stands (clustered inputs whose extent / spacing
+//    ratio exceeds 2^32, or non-finite coordinates, take this path).
+// Either way the result is THE sorted order by (coordinate, id): bit-exact tree, 3.2x less sort traffic normally.
 //
 // This replaces, together with build.cu, the random-pivot quick-select of the reference
 // (Parallel/RustVersion/src/quickstat.rs:9-34 called from array_kd_tree.rs:561-562): with the three lists
 // sorted once per step, every node's median is the middle entry of its list segment and the bounding box
 // is its two ends.
 #include <algorithm>
+#include <cstdlib>
 
 #include "ctx.cuh"
 
@@ -17,16 +28,35 @@ struct Pos3 {
   const double* p[3];
 };
 
+// sort state (device): [0..2] min key64, [3..5] max key64 (flat_detect), [6..8] lo, [9..11] scale as f64 bits
+// (sort_prep), [12] need64
+constexpr int SS_MIN = 0, SS_MAX = 3, SS_LO = 6, SS_SCALE = 9, SS_NEED64 = 12, SS_WORDS = 16;
+
+__device__ __forceinline__ double key_to_f64(uint64_t k) {  // inverse of f64_key
+  const uint64_t u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)u);
+}
+// the sort key of coordinate x in pass family K: the full order-preserving image, or its monotone 32-bit quantisation
+template <typename K>
+__device__ __forceinline__ K sort_key(double x, const uint64_t* __restrict__ ss, int d) {
+  if (sizeof(K) == 8) return (K)f64_key(x);
+  const double lo = __longlong_as_double((long long)ss[SS_LO + d]);
+  const double scale = __longlong_as_double((long long)ss[SS_SCALE + d]);
+  return (K)__double2uint_rz(__dmul_rn(__dsub_rn(x, lo), scale));  // saturating; monotone non-decreasing in x
+}
+
 // ---- pass kernel 1: per-tile digit histogram
-template <bool FIRST>
-__global__ void __launch_bounds__(SORT_THREADS) sort_upsweep(Pos3 pos, const uint64_t* __restrict__ keys_in,
+template <bool FIRST, typename K>
+__global__ void __launch_bounds__(SORT_THREADS) sort_upsweep(Pos3 pos, const K* __restrict__ keys_in,
                                                              uint32_t n, int shift, uint32_t ntiles,
                                                              uint32_t* __restrict__ hist,
-                                                             const uint32_t* __restrict__ flat) {
+                                                             const uint32_t* __restrict__ flat,
+                                                             const uint64_t* __restrict__ ss) {
   pdl_sync();
   __shared__ uint32_t h[256];
   const int d = blockIdx.y;
   if (flat[d]) return;  // all coordinates of this dimension are equal: its list is never consulted (build.cu)
+  if (sizeof(K) == 8 && !ss[SS_NEED64]) return;  // the 32-bit result stands
   const uint32_t tile = blockIdx.x;
   h[threadIdx.x] = 0;
   __syncthreads();
@@ -35,8 +65,8 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_upsweep(Pos3 pos, const uin
   for (int k = 0; k < SORT_IPT; ++k) {
     uint64_t i = base + (uint64_t)k * SORT_THREADS + threadIdx.x;
     if (i < n) {
-      uint64_t key = FIRST ? f64_key(pos.p[d][i]) : keys_in[(uint64_t)d * n + i];
-      atomicAdd(&h[(key >> shift) & 255u], 1u);
+      K key = FIRST ? sort_key<K>(pos.p[d][i], ss, d) : keys_in[(uint64_t)d * n + i];
+      atomicAdd(&h[(uint32_t)(key >> shift) & 255u], 1u);
     }
   }
   __syncthreads();
@@ -44,12 +74,15 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_upsweep(Pos3 pos, const uin
 }
 
 // ---- pass kernel 2: exclusive scan of every (dimension, digit) row over tiles; row totals to tot[]
+template <bool GATED>
 __global__ void __launch_bounds__(256) sort_scan_rows(uint32_t* __restrict__ hist, uint32_t ntiles,
                                                       uint32_t* __restrict__ tot,
-                                                      const uint32_t* __restrict__ flat) {
+                                                      const uint32_t* __restrict__ flat,
+                                                      const uint64_t* __restrict__ ss) {
   pdl_sync();
   __shared__ uint32_t wsum[8];
   if (flat[blockIdx.y]) return;
+  if (GATED && !ss[SS_NEED64]) return;
   uint32_t* row = hist + ((uint64_t)blockIdx.y * 256 + blockIdx.x) * ntiles;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint32_t carry = 0;
@@ -79,24 +112,26 @@ __global__ void __launch_bounds__(256) sort_scan_rows(uint32_t* __restrict__ his
 }
 
 // ---- pass kernel 3: stable rank inside the tile (warp match), scatter
-template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const uint64_t* __restrict__ keys_in,
+template <bool FIRST, bool LAST, typename K>
+__global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const K* __restrict__ keys_in,
                                                                const uint32_t* __restrict__ vals_in,
-                                                               uint64_t* __restrict__ keys_out,
+                                                               K* __restrict__ keys_out,
                                                                uint32_t* __restrict__ vals_out, uint32_t n,
                                                                int shift, uint32_t ntiles,
                                                                const uint32_t* __restrict__ hist,
                                                                const uint32_t* __restrict__ tot,
-                                                               const uint32_t* __restrict__ flat) {
+                                                               const uint32_t* __restrict__ flat,
+                                                               const uint64_t* __restrict__ ss) {
   pdl_sync();
   __shared__ uint32_t wcnt[SORT_THREADS / 32][256];
   __shared__ uint32_t base[256];
   __shared__ uint32_t toff[256];
   __shared__ uint32_t wsum[8];
-  __shared__ uint64_t skey[SORT_TILE];
+  __shared__ K skey[SORT_TILE];
   __shared__ uint32_t sval[SORT_TILE];
   const int d = blockIdx.y;
   if (flat[d]) return;
+  if (sizeof(K) == 8 && !ss[SS_NEED64]) return;
   const uint32_t tile = blockIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
@@ -121,14 +156,14 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const u
   }
   __syncthreads();
 
-  uint64_t key[SORT_IPT];
+  K key[SORT_IPT];
   uint32_t val[SORT_IPT], rk[SORT_IPT];
   const uint64_t start = (uint64_t)tile * SORT_TILE + (uint64_t)w * (32 * SORT_IPT);
 #pragma unroll
   for (int r = 0; r < SORT_IPT; ++r) {
     uint64_t i = start + r * 32 + lane;
     bool valid = i < n;
-    key[r] = valid ? (FIRST ? f64_key(pos.p[d][i]) : keys_in[(uint64_t)d * n + i]) : ~0ull;
+    key[r] = valid ? (FIRST ? sort_key<K>(pos.p[d][i], ss, d) : keys_in[(uint64_t)d * n + i]) : (K)~(K)0;
     val[r] = valid ? (FIRST ? (uint32_t)i : vals_in[(uint64_t)d * n + i]) : 0u;
     uint32_t dg = valid ? (uint32_t)((key[r] >> shift) & 255u) : 256u;
     uint32_t peers = __match_any_sync(0xffffffffu, dg);
@@ -185,7 +220,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const u
   for (int k = 0; k < SORT_IPT; ++k) {
     const uint32_t p = k * SORT_THREADS + threadIdx.x;
     if (p < nvalid) {
-      const uint64_t kk = skey[p];
+      const K kk = skey[p];
       const uint32_t dg = (uint32_t)((kk >> shift) & 255u);
       const uint64_t dst = (uint64_t)d * n + base[dg] + (p - toff[dg]);
       if (!LAST) keys_out[dst] = kk;
@@ -198,24 +233,123 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const u
 // ever).  Such a dimension has extent 0 in every node, so it is never the split dimension (array_kd_tree.rs:551-556
 // keeps the lower dimension on ties) and its sorted list is never consulted: sorting and partitioning it is skipped.
 // Dimension 0 is always kept — it is the tie winner when all extents are 0 and it orders the leaves.
-__global__ void flat_init(uint32_t* flat) {
+__global__ void flat_init(uint32_t* flat, uint64_t* ss) {
   pdl_sync();
   if (threadIdx.x < 4) flat[threadIdx.x] = threadIdx.x > 0 ? 1u : 0u;
+  if (threadIdx.x < 3) {
+    ss[SS_MIN + threadIdx.x] = ~0ull;
+    ss[SS_MAX + threadIdx.x] = 0ull;
+  }
+  if (threadIdx.x == 0) ss[SS_NEED64] = 0ull;
 }
 // flat[3] = 1 when, in addition, every z is +-0 and every mass is > 0: then every node's centre-of-mass z
 // (sum m*z / sum m) is +-0 as well, dz == 0 in every test and interaction, and the walk skips the z terms (walk2.cuh).
+// The same pass reduces the extreme keys of every dimension (the range the 32-bit sort keys are scaled to).
 __global__ void __launch_bounds__(256) flat_detect(Pos3 pos, const double* __restrict__ mass, uint32_t n,
-                                                   uint32_t* __restrict__ flat) {
+                                                   uint32_t* __restrict__ flat, uint64_t* __restrict__ ss) {
   pdl_sync();
-  const int d = blockIdx.y + 1;
+  __shared__ uint64_t smin[8], smax[8];
+  const int d = blockIdx.y;
   const uint64_t k0 = f64_key(pos.p[d][0]);
   bool differs = false, heavy = true;
+  uint64_t kmin = ~0ull, kmax = 0ull;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    differs |= f64_key(pos.p[d][i]) != k0;
+    const uint64_t k = f64_key(pos.p[d][i]);
+    differs |= k != k0;
+    kmin = k < kmin ? k : kmin;
+    kmax = k > kmax ? k : kmax;
     if (d == 2) heavy &= mass[i] > 0.0;
   }
-  if (differs) flat[d] = 0u;
+  if (d > 0 && differs) flat[d] = 0u;
   if (d == 2 && (differs || !heavy || k0 != f64_key(0.0))) flat[3] = 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint64_t a = __shfl_xor_sync(0xffffffffu, kmin, o), b = __shfl_xor_sync(0xffffffffu, kmax, o);
+    kmin = a < kmin ? a : kmin;
+    kmax = b > kmax ? b : kmax;
+  }
+  if ((threadIdx.x & 31) == 0) smin[threadIdx.x >> 5] = kmin, smax[threadIdx.x >> 5] = kmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) {
+      kmin = smin[k] < kmin ? smin[k] : kmin;
+      kmax = smax[k] > kmax ? smax[k] : kmax;
+    }
+    atomicMin(reinterpret_cast<unsigned long long*>(&ss[SS_MIN + d]), (unsigned long long)kmin);
+    atomicMax(reinterpret_cast<unsigned long long*>(&ss[SS_MAX + d]), (unsigned long long)kmax);
+  }
+}
+// lo / scale of the 32-bit keys; non-finite extremes (inf or NaN coordinates) go straight to the 64-bit sort
+__global__ void sort_prep(uint64_t* ss) {
+  pdl_sync();
+  const int d = threadIdx.x;
+  if (d >= 3) return;
+  const double lo = key_to_f64(ss[SS_MIN + d]), hi = key_to_f64(ss[SS_MAX + d]);
+  double scale = 0.0;  // all keys 0 when the extent is 0: one run of equal coordinates, already in id order
+  if (!(fabs(lo) <= 1.7976931348623157e308) || !(fabs(hi) <= 1.7976931348623157e308)) {
+    ss[SS_NEED64] = 1ull;
+  } else if (hi > lo) {
+    scale = 4294967295.0 / (hi - lo);  // (hi - lo) may overflow to inf: scale 0, handled like extent 0 + fix-up
+  }
+  ss[SS_LO + d] = (uint64_t)__double_as_longlong(lo);
+  ss[SS_SCALE + d] = (uint64_t)__double_as_longlong(scale);
+}
+
+// Orders every run of equal key32 by (key64, id).  The 32-bit sort left each run in ascending id order, so a run is
+// already right when its key64 are non-decreasing.  Run starts with <= FIX_CAP entries sort their run (stable insertion
+// sort on key64, almost always a single compare of a pair); every other entry checks the pair (i-1, i) and, if that
+// pair is out of order inside a run longer than FIX_CAP, requests the 64-bit sort.
+constexpr int FIX_CAP = 32;
+__global__ void __launch_bounds__(256) sort_fixup(Pos3 pos, const uint32_t* __restrict__ keys, uint32_t* __restrict__ lists,
+                                                  uint32_t n, const uint32_t* __restrict__ flat,
+                                                  uint64_t* __restrict__ ss) {
+  pdl_sync();
+  const int d = blockIdx.y;
+  if (flat[d] || ss[SS_NEED64]) return;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t* key = keys + (uint64_t)d * n;
+  uint32_t* lst = lists + (uint64_t)d * n;
+  const double* x = pos.p[d];
+  const uint32_t k = key[i];
+  const bool start = i == 0 || key[i - 1] != k;
+  if (start) {
+    if (i + 1 >= n || key[i + 1] != k) return;  // singleton
+    uint32_t len = 2;
+    while (len <= FIX_CAP && i + len < n && key[i + len] == k) ++len;
+    if (len > FIX_CAP) return;  // long run: verified pair by pair by its members
+    if (len == 2) {
+      const uint32_t a = lst[i], b = lst[i + 1];
+      if (f64_key(x[a]) > f64_key(x[b])) lst[i] = b, lst[i + 1] = a;
+      return;
+    }
+    uint32_t ids[FIX_CAP];
+    uint64_t ks[FIX_CAP];
+    bool moved = false;
+    for (uint32_t r = 0; r < len; ++r) {
+      const uint32_t id = lst[i + r];
+      const uint64_t kk = f64_key(x[id]);
+      int j = (int)r - 1;
+      while (j >= 0 && ks[j] > kk) {
+        ks[j + 1] = ks[j];
+        ids[j + 1] = ids[j];
+        --j;
+        moved = true;
+      }
+      ks[j + 1] = kk;
+      ids[j + 1] = id;
+    }
+    if (moved)
+      for (uint32_t r = 0; r < len; ++r) lst[i + r] = ids[r];
+  } else {
+    const uint32_t a = lst[i - 1], b = lst[i];
+    if (f64_key(x[a]) <= f64_key(x[b])) return;
+    // out of order (or caught mid-update of a short run, which its start thread finishes): long run?
+    uint32_t s = i, e = i + 1;
+    while (s > 0 && i - s <= FIX_CAP && key[s - 1] == k) --s;
+    while (e < n && e - s <= FIX_CAP && key[e] == k) ++e;
+    if (e - s > FIX_CAP) ss[SS_NEED64] = 1ull;
+  }
 }
 
 // rk[d][id] = rank of particle id in the sorted list of dimension d (read by the global partition levels, build.cu)
@@ -228,34 +362,53 @@ __global__ void __launch_bounds__(256) rank_from_lists(const uint32_t* __restric
   if (i < n) rk[(uint64_t)d * n + lists[(uint64_t)d * n + i]] = i;
 }
 
-// Sorted lists end in c->list[0] (8 passes: positions -> buf1 -> buf0 -> ... -> buf0).
-int sort_lists(Ctx* c) {
+// Sorted lists end in c->list[0] (32-bit keys: positions -> buf1 -> buf0 -> buf1 -> buf0; 64-bit keys: 8 passes,
+// same parity).  The 64-bit kernels return at once unless need64 was raised.
+template <typename K>
+static void sort_passes(Ctx* c, Pos3 pos) {
   const uint32_t n = (uint32_t)c->n;
   const uint32_t nt = c->ntiles;
-  Pos3 pos = {{c->pos[0], c->pos[1], c->pos[2]}};
+  const int passes = (int)sizeof(K);
   dim3 gt(nt, 3), gs(256, 3);
-  KDNB_LAUNCH(c, flat_init, 1, 32, 0, c->flat);
-  KDNB_LAUNCH(c, flat_detect, dim3(std::min<uint32_t>((n + 255) / 256, 1184u), 2), 256, 0, pos, c->mass, n, c->flat);
-  for (int pass = 0; pass < 8; ++pass) {
+  K* kb[2] = {reinterpret_cast<K*>(c->keys[0]), reinterpret_cast<K*>(c->keys[1])};
+  for (int pass = 0; pass < passes; ++pass) {
     const int shift = 8 * pass;
     const int src = (pass & 1) ? 1 : 0, dst = src ^ 1;  // pass 0 reads positions, writes buf1
     if (pass == 0) {
-      KDNB_LAUNCH(c, sort_upsweep<true>, gt, SORT_THREADS, 0, pos, nullptr, n, shift, nt, c->hist, c->flat);
+      KDNB_LAUNCH(c, (sort_upsweep<true, K>), gt, SORT_THREADS, 0, pos, nullptr, n, shift, nt, c->hist, c->flat, c->sort_state);
     } else {
-      KDNB_LAUNCH(c, sort_upsweep<false>, gt, SORT_THREADS, 0, pos, c->keys[src], n, shift, nt, c->hist, c->flat);
+      KDNB_LAUNCH(c, (sort_upsweep<false, K>), gt, SORT_THREADS, 0, pos, kb[src], n, shift, nt, c->hist, c->flat, c->sort_state);
     }
-    KDNB_LAUNCH(c, sort_scan_rows, gs, 256, 0, c->hist, nt, c->digit_tot, c->flat);
+    KDNB_LAUNCH(c, sort_scan_rows<sizeof(K) == 8>, gs, 256, 0, c->hist, nt, c->digit_tot, c->flat, c->sort_state);
     if (pass == 0) {
-      KDNB_LAUNCH(c, (sort_downsweep<true, false>), gt, SORT_THREADS, 0, pos, nullptr, nullptr, c->keys[1],
-                  c->list[1], n, shift, nt, c->hist, c->digit_tot, c->flat);
-    } else if (pass == 7) {
-      KDNB_LAUNCH(c, (sort_downsweep<false, true>), gt, SORT_THREADS, 0, pos, c->keys[src], c->list[src],
-                  c->keys[dst], c->list[dst], n, shift, nt, c->hist, c->digit_tot, c->flat);
+      KDNB_LAUNCH(c, (sort_downsweep<true, false, K>), gt, SORT_THREADS, 0, pos, nullptr, nullptr, kb[1], c->list[1], n,
+                  shift, nt, c->hist, c->digit_tot, c->flat, c->sort_state);
+    } else if (pass == passes - 1 && sizeof(K) == 8) {  // (the 32-bit keys of the last pass are read by sort_fixup)
+      KDNB_LAUNCH(c, (sort_downsweep<false, true, K>), gt, SORT_THREADS, 0, pos, kb[src], c->list[src], kb[dst],
+                  c->list[dst], n, shift, nt, c->hist, c->digit_tot, c->flat, c->sort_state);
     } else {
-      KDNB_LAUNCH(c, (sort_downsweep<false, false>), gt, SORT_THREADS, 0, pos, c->keys[src], c->list[src],
-                  c->keys[dst], c->list[dst], n, shift, nt, c->hist, c->digit_tot, c->flat);
+      KDNB_LAUNCH(c, (sort_downsweep<false, false, K>), gt, SORT_THREADS, 0, pos, kb[src], c->list[src], kb[dst],
+                  c->list[dst], n, shift, nt, c->hist, c->digit_tot, c->flat, c->sort_state);
     }
   }
+}
+
+int sort_lists(Ctx* c) {
+  const uint32_t n = (uint32_t)c->n;
+  Pos3 pos = {{c->pos[0], c->pos[1], c->pos[2]}};
+  static const bool only64 = getenv("KDNB_SORT64") != nullptr;  // profiling knob: skip the 32-bit path
+  KDNB_LAUNCH(c, flat_init, 1, 32, 0, c->flat, c->sort_state);
+  KDNB_LAUNCH(c, flat_detect, dim3(std::min<uint32_t>((n + 255) / 256, 1184u), 3), 256, 0, pos, c->mass, n, c->flat,
+              c->sort_state);
+  KDNB_LAUNCH(c, sort_prep, 1, 32, 0, c->sort_state);
+  if (only64) {
+    KDNB_CUDA_TRY(c, cudaMemsetAsync(c->sort_state + SS_NEED64, 1, 1, c->stream));
+  } else {
+    sort_passes<uint32_t>(c, pos);
+    KDNB_LAUNCH(c, sort_fixup, dim3((n + 255) / 256, 3), 256, 0, pos, reinterpret_cast<const uint32_t*>(c->keys[0]),
+                c->list[0], n, c->flat, c->sort_state);
+  }
+  sort_passes<uint64_t>(c, pos);
   if (c->l0 > 0) KDNB_LAUNCH(c, rank_from_lists, dim3((n + 255) / 256, 3), 256, 0, c->list[0], n, c->rk, c->flat);
   KDNB_CHECK_LAUNCH(c);
   return 0;

@@ -134,6 +134,57 @@ def test_build_3d_and_ties_bit_exact(orc, n, quant):
     assert set(np.unique(gnodes["split_dim"][gnodes["kind"] == kd.INTERNAL])) == {0, 1, 2}
 
 
+def _clustered(n, seed, kind):
+    """Inputs that defeat the 32-bit sort keys (sort.cu): far more distinct coordinates than 2^-32 of the extent
+    can separate, so whole runs share a key32 and the build has to fall back on (or fix up with) the full 64-bit order."""
+    rng = np.random.default_rng(seed)
+    parts = cube(n, seed=seed, equal_mass=False)
+    if kind == "tight_cluster_far_outlier":        # all but one particle within 1e-9 of each other, one at 1e3
+        parts["p"] = 1.0 + rng.random((n, 3)) * 1e-9
+        parts["p"][n // 2] = (1e3, -1e3, 5e2)
+    elif kind == "two_scales":                     # half the particles in a 1e-8 ball, half spread over [-1, 1)
+        parts["p"][: n // 2] = 0.25 + rng.random((n // 2, 3)) * 1e-8
+    elif kind == "huge_extent":                    # hi - lo overflows to inf
+        parts["p"][0] = (1.5e308, 1.5e308, 1.5e308)
+        parts["p"][1] = (-1.5e308, -1.5e308, -1.5e308)
+    elif kind == "pairs":                          # neighbours one ulp apart, in descending id order
+        base = np.sort(rng.random(n // 2) * 2.0 - 1.0)
+        x = np.empty(n)
+        x[0::2] = np.nextafter(base, 2.0)
+        x[1::2] = base
+        parts["p"][:, 0] = x
+    return parts
+
+
+@pytest.mark.parametrize("kind", ["tight_cluster_far_outlier", "two_scales", "huge_extent", "pairs"])
+def test_build_inputs_beyond_32_bit_keys_bit_exact(orc, kind):
+    parts = _clustered(30000, seed=11, kind=kind)
+    with kd.KDTreeSim() as sim:
+        sim.upload(parts)
+        sim.build_tree()
+        gnodes, gidx = sim.tree()
+    onodes, oidx, _ = orc.build_tree_canonical(parts, threads=4)
+    assert_tree_bit_exact(orc, gnodes, gidx, onodes, oidx, 8)
+
+
+def test_build_forced_64_bit_sort_matches():
+    """KDNB_SORT64=1 skips the 32-bit passes: both key widths must produce the same tree."""
+    import subprocess, sys
+    code = ("import numpy as np, multilanguagekdtree_b200 as kd\n"
+            "p = kd.circular_orbits(50000, seed=5)\n"
+            "s = kd.KDTreeSim(); s.upload(p); s.build_tree(); n, i = s.tree()\n"
+            "np.save(__import__('sys').argv[1], i)\n")
+    import tempfile, os
+    with tempfile.TemporaryDirectory() as d:
+        out = {}
+        for tag, env in (("k32", {}), ("k64", {"KDNB_SORT64": "1"})):
+            f = os.path.join(d, tag + ".npy")
+            subprocess.run([sys.executable, "-c", code, f], check=True, env={**os.environ, **env},
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            out[tag] = np.load(f)
+        assert np.array_equal(out["k32"], out["k64"])
+
+
 def test_build_vs_faithful_reference_order(orc):
     """Against the reference's own summation order (random pivots): everything order-independent is bit-exact,
     m / cm agree to the reference's run-to-run noise."""
