@@ -281,14 +281,17 @@ def run_kdnb(args) -> None:
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {
-                "workload": workload_name(n), "parallelism": f"replicated tree, walk sharded over {world} GPU(s) by tree-ordered ranges, ncclAllGather of accelerations",
-                "l2": "no explicit flush: every step streams ~0.9 GB (8-pass radix-sort ping-pong, 3 dims) through the 126 MB L2 before the walk",
+                "workload": workload_name(n), "parallelism": f"replicated tree, walk sharded over {world} GPU(s) by tree-ordered ranges, accelerations exchanged by peer stores over NVLink from inside the walk kernel (ncclAllGather fallback)",
+                "l2": "no explicit flush: at N=1M every step streams ~0.5 GB (radix-sort ping-pong, level partitions, bottom build) through the 126 MB L2 before the walk; at N>=10M the inputs themselves exceed L2",
                 "timer": "CUDA events on the library's stream around K steps (step replayed as a CUDA graph), max over ranks; stage_ms from a second, profiled context (plain launches)",
             },
             "stage_ms_per_step": {"build": build_ms, "walk": walk_ms, "kick": kick_ms, "exchange": exch_ms},
             "roofline": {
-                "kernel": "walk_kernel", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                "kernel": "walk2_kernel", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": achieved / fp64_peak if fp64_peak else None,
+                # DRAM bytes of one launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu capture
+                # profiles/r01_launches_*.csv; measured at N=1M on one GPU only
+                "traffic": 56.5e6 if (n == 1_000_000 and world == 1) else None,
                 "peak_source": "DFMA-chain microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)",
                 "flops_per_particle_step": flops_step / (n + 1),
                 "counts_per_particle": {"node_tests": V / (n + 1), "accepts": A / (n + 1), "leaf_visits": LV / (n + 1), "pairs": P / (n + 1)},

@@ -37,6 +37,7 @@ struct Ctx {
   double theta = 0.3, theta2 = 0.09;
   uint32_t flags = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side_stream = nullptr;  // captures conditional-node bodies (sort.cu)
 
   // sizes
   uint64_t n = 0;        // particles (N+1 of the reference)

@@ -389,6 +389,7 @@ kdnb_ctx* kdnb_create(const kdnb_config* cfg) {
   c->flags = k.flags;
   if ((e = cudaSetDevice(c->device)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&c->sw_begin)) != cudaSuccess || (e = cudaEventCreate(&c->sw_end)) != cudaSuccess) {
     g_create_error = std::string("CUDA init: ") + cudaGetErrorString(e);
     delete h;
@@ -412,6 +413,7 @@ void kdnb_destroy(kdnb_ctx* ctx) {
   if (c->sw_begin) cudaEventDestroy(c->sw_begin);
   if (c->sw_end) cudaEventDestroy(c->sw_end);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->side_stream) cudaStreamDestroy(c->side_stream);
   delete ctx;
 }
 

@@ -19,6 +19,7 @@
 // is its two ends.
 #include <algorithm>
 #include <cstdlib>
+#include <string>
 
 #include "ctx.cuh"
 
@@ -51,12 +52,12 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_upsweep(Pos3 pos, const K* 
                                                              uint32_t n, int shift, uint32_t ntiles,
                                                              uint32_t* __restrict__ hist,
                                                              const uint32_t* __restrict__ flat,
-                                                             const uint64_t* __restrict__ ss) {
+                                                             const uint64_t* __restrict__ ss, bool gated) {
   pdl_sync();
   __shared__ uint32_t h[256];
   const int d = blockIdx.y;
   if (flat[d]) return;  // all coordinates of this dimension are equal: its list is never consulted (build.cu)
-  if (sizeof(K) == 8 && !ss[SS_NEED64]) return;  // the 32-bit result stands
+  if (gated && !ss[SS_NEED64]) return;  // the 32-bit result stands
   const uint32_t tile = blockIdx.x;
   h[threadIdx.x] = 0;
   __syncthreads();
@@ -74,15 +75,14 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_upsweep(Pos3 pos, const K* 
 }
 
 // ---- pass kernel 2: exclusive scan of every (dimension, digit) row over tiles; row totals to tot[]
-template <bool GATED>
 __global__ void __launch_bounds__(256) sort_scan_rows(uint32_t* __restrict__ hist, uint32_t ntiles,
                                                       uint32_t* __restrict__ tot,
                                                       const uint32_t* __restrict__ flat,
-                                                      const uint64_t* __restrict__ ss) {
+                                                      const uint64_t* __restrict__ ss, bool gated) {
   pdl_sync();
   __shared__ uint32_t wsum[8];
   if (flat[blockIdx.y]) return;
-  if (GATED && !ss[SS_NEED64]) return;
+  if (gated && !ss[SS_NEED64]) return;
   uint32_t* row = hist + ((uint64_t)blockIdx.y * 256 + blockIdx.x) * ntiles;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint32_t carry = 0;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const K
                                                                const uint32_t* __restrict__ hist,
                                                                const uint32_t* __restrict__ tot,
                                                                const uint32_t* __restrict__ flat,
-                                                               const uint64_t* __restrict__ ss) {
+                                                               const uint64_t* __restrict__ ss, bool gated) {
   pdl_sync();
   __shared__ uint32_t wcnt[SORT_THREADS / 32][256];
   __shared__ uint32_t base[256];
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const K
   __shared__ uint32_t sval[SORT_TILE];
   const int d = blockIdx.y;
   if (flat[d]) return;
-  if (sizeof(K) == 8 && !ss[SS_NEED64]) return;
+  if (gated && !ss[SS_NEED64]) return;
   const uint32_t tile = blockIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
@@ -362,53 +362,130 @@ __global__ void __launch_bounds__(256) rank_from_lists(const uint32_t* __restric
   if (i < n) rk[(uint64_t)d * n + lists[(uint64_t)d * n + i]] = i;
 }
 
+// hands need64 to the conditional node that holds the 64-bit passes (graph replay)
+__global__ void sort_set_cond(cudaGraphConditionalHandle h, const uint64_t* __restrict__ ss) {
+  pdl_sync();
+  cudaGraphSetConditional(h, ss[SS_NEED64] ? 1u : 0u);
+}
+
 // Sorted lists end in c->list[0] (32-bit keys: positions -> buf1 -> buf0 -> buf1 -> buf0; 64-bit keys: 8 passes,
-// same parity).  The 64-bit kernels return at once unless need64 was raised.
+// same parity).
 template <typename K>
-static void sort_passes(Ctx* c, Pos3 pos) {
+static void sort_passes(Ctx* c, Pos3 pos, bool gated) {
   const uint32_t n = (uint32_t)c->n;
   const uint32_t nt = c->ntiles;
   const int passes = (int)sizeof(K);
   dim3 gt(nt, 3), gs(256, 3);
   K* kb[2] = {reinterpret_cast<K*>(c->keys[0]), reinterpret_cast<K*>(c->keys[1])};
+  const uint64_t* ss = c->sort_state;
   for (int pass = 0; pass < passes; ++pass) {
     const int shift = 8 * pass;
     const int src = (pass & 1) ? 1 : 0, dst = src ^ 1;  // pass 0 reads positions, writes buf1
     if (pass == 0) {
-      KDNB_LAUNCH(c, (sort_upsweep<true, K>), gt, SORT_THREADS, 0, pos, nullptr, n, shift, nt, c->hist, c->flat, c->sort_state);
+      KDNB_LAUNCH(c, (sort_upsweep<true, K>), gt, SORT_THREADS, 0, pos, nullptr, n, shift, nt, c->hist, c->flat, ss, gated);
     } else {
-      KDNB_LAUNCH(c, (sort_upsweep<false, K>), gt, SORT_THREADS, 0, pos, kb[src], n, shift, nt, c->hist, c->flat, c->sort_state);
+      KDNB_LAUNCH(c, (sort_upsweep<false, K>), gt, SORT_THREADS, 0, pos, kb[src], n, shift, nt, c->hist, c->flat, ss, gated);
     }
-    KDNB_LAUNCH(c, sort_scan_rows<sizeof(K) == 8>, gs, 256, 0, c->hist, nt, c->digit_tot, c->flat, c->sort_state);
+    KDNB_LAUNCH(c, sort_scan_rows, gs, 256, 0, c->hist, nt, c->digit_tot, c->flat, ss, gated);
     if (pass == 0) {
       KDNB_LAUNCH(c, (sort_downsweep<true, false, K>), gt, SORT_THREADS, 0, pos, nullptr, nullptr, kb[1], c->list[1], n,
-                  shift, nt, c->hist, c->digit_tot, c->flat, c->sort_state);
+                  shift, nt, c->hist, c->digit_tot, c->flat, ss, gated);
     } else if (pass == passes - 1 && sizeof(K) == 8) {  // (the 32-bit keys of the last pass are read by sort_fixup)
       KDNB_LAUNCH(c, (sort_downsweep<false, true, K>), gt, SORT_THREADS, 0, pos, kb[src], c->list[src], kb[dst],
-                  c->list[dst], n, shift, nt, c->hist, c->digit_tot, c->flat, c->sort_state);
+                  c->list[dst], n, shift, nt, c->hist, c->digit_tot, c->flat, ss, gated);
     } else {
       KDNB_LAUNCH(c, (sort_downsweep<false, false, K>), gt, SORT_THREADS, 0, pos, kb[src], c->list[src], kb[dst],
-                  c->list[dst], n, shift, nt, c->hist, c->digit_tot, c->flat, c->sort_state);
+                  c->list[dst], n, shift, nt, c->hist, c->digit_tot, c->flat, ss, gated);
     }
   }
+}
+
+// The 64-bit passes as the body of an IF node of the graph being captured on c->stream (condition: need64), so a
+// replayed step pays for them only when they are needed.  Returns false when nothing was added (the caller then
+// falls back on gated launches).
+static bool sort64_conditional(Ctx* c, Pos3 pos) {
+  if (!c->side_stream) return false;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaGraph_t g = nullptr;
+  const cudaGraphNode_t* deps = nullptr;
+  size_t nd = 0;
+  if (cudaStreamGetCaptureInfo(c->stream, &st, nullptr, &g, &deps, &nd) != cudaSuccess ||
+      st != cudaStreamCaptureStatusActive || !g) {
+    cudaGetLastError();
+    return false;
+  }
+  cudaGraphConditionalHandle h;
+  if (cudaGraphConditionalHandleCreate(&h, g, 0, cudaGraphCondAssignDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  KDNB_LAUNCH(c, sort_set_cond, 1, 1, 0, h, (const uint64_t*)c->sort_state);
+  if (cudaStreamGetCaptureInfo(c->stream, &st, nullptr, &g, &deps, &nd) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  cudaGraphNodeParams p = {};
+  p.type = cudaGraphNodeTypeConditional;
+  p.conditional.handle = h;
+  p.conditional.type = cudaGraphCondTypeIf;
+  p.conditional.size = 1;
+  cudaGraphNode_t node = nullptr;
+  if (cudaGraphAddNode(&node, g, deps, nd, &p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  cudaGraph_t body = p.conditional.phGraph_out[0];
+  bool ok = cudaStreamBeginCaptureToGraph(c->side_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) ==
+            cudaSuccess;
+  if (ok) {
+    cudaStream_t keep = c->stream;
+    const uint64_t l0 = c->launches;
+    c->stream = c->side_stream;
+    sort_passes<uint64_t>(c, pos, false);
+    c->stream = keep;
+    c->launches = l0;  // not launched unless need64 is raised
+    cudaGraph_t out = nullptr;
+    ok = cudaStreamEndCapture(c->side_stream, &out) == cudaSuccess;
+  }
+  // the main capture continues after the conditional node (an empty body is harmless if its capture failed, but
+  // then the gated launches must follow)
+  if (cudaStreamUpdateCaptureDependencies(c->stream, &node, 1, cudaStreamSetCaptureDependencies) != cudaSuccess) ok = false;
+  if (!ok) cudaGetLastError();
+  return ok;
 }
 
 int sort_lists(Ctx* c) {
   const uint32_t n = (uint32_t)c->n;
   Pos3 pos = {{c->pos[0], c->pos[1], c->pos[2]}};
-  static const bool only64 = getenv("KDNB_SORT64") != nullptr;  // profiling knob: skip the 32-bit path
+  // KDNB_SORT: "64" = skip the 32-bit path; "stubs" = always launch the 64-bit passes gated on need64
+  static const char* knob = getenv("KDNB_SORT");
+  static const bool only64 = knob && std::string(knob) == "64";
+  static const bool stubs = knob && std::string(knob) == "stubs";
   KDNB_LAUNCH(c, flat_init, 1, 32, 0, c->flat, c->sort_state);
   KDNB_LAUNCH(c, flat_detect, dim3(std::min<uint32_t>((n + 255) / 256, 1184u), 3), 256, 0, pos, c->mass, n, c->flat,
               c->sort_state);
   KDNB_LAUNCH(c, sort_prep, 1, 32, 0, c->sort_state);
   if (only64) {
-    KDNB_CUDA_TRY(c, cudaMemsetAsync(c->sort_state + SS_NEED64, 1, 1, c->stream));
+    sort_passes<uint64_t>(c, pos, false);
   } else {
-    sort_passes<uint32_t>(c, pos);
+    sort_passes<uint32_t>(c, pos, false);
     KDNB_LAUNCH(c, sort_fixup, dim3((n + 255) / 256, 3), 256, 0, pos, reinterpret_cast<const uint32_t*>(c->keys[0]),
                 c->list[0], n, c->flat, c->sort_state);
+    // the 64-bit passes run only when need64 was raised: decided by the host between plain launches (one stream
+    // synchronisation), by a conditional node inside a captured step, by the kernels themselves otherwise
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    KDNB_CUDA_TRY(c, cudaStreamIsCapturing(c->stream, &st));
+    if (st == cudaStreamCaptureStatusActive) {
+      if (stubs || c->use_pdl || !sort64_conditional(c, pos)) sort_passes<uint64_t>(c, pos, true);
+    } else if (stubs || c->use_pdl) {
+      sort_passes<uint64_t>(c, pos, true);
+    } else {
+      uint64_t need = 0;
+      KDNB_CUDA_TRY(c, cudaMemcpyAsync(&need, c->sort_state + SS_NEED64, sizeof(need), cudaMemcpyDeviceToHost, c->stream));
+      KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      if (need) sort_passes<uint64_t>(c, pos, false);
+    }
   }
-  sort_passes<uint64_t>(c, pos);
   if (c->l0 > 0) KDNB_LAUNCH(c, rank_from_lists, dim3((n + 255) / 256, 3), 256, 0, c->list[0], n, c->rk, c->flat);
   KDNB_CHECK_LAUNCH(c);
   return 0;

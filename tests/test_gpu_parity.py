@@ -168,7 +168,7 @@ def test_build_inputs_beyond_32_bit_keys_bit_exact(orc, kind):
 
 
 def test_build_forced_64_bit_sort_matches():
-    """KDNB_SORT64=1 skips the 32-bit passes: both key widths must produce the same tree."""
+    """KDNB_SORT=64 skips the 32-bit passes, KDNB_SORT=stubs launches gated 64-bit passes: same tree every way."""
     import subprocess, sys
     code = ("import numpy as np, multilanguagekdtree_b200 as kd\n"
             "p = kd.circular_orbits(50000, seed=5)\n"
@@ -177,12 +177,12 @@ def test_build_forced_64_bit_sort_matches():
     import tempfile, os
     with tempfile.TemporaryDirectory() as d:
         out = {}
-        for tag, env in (("k32", {}), ("k64", {"KDNB_SORT64": "1"})):
+        for tag, env in (("k32", {}), ("k64", {"KDNB_SORT": "64"}), ("stubs", {"KDNB_SORT": "stubs"})):
             f = os.path.join(d, tag + ".npy")
             subprocess.run([sys.executable, "-c", code, f], check=True, env={**os.environ, **env},
                            cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
             out[tag] = np.load(f)
-        assert np.array_equal(out["k32"], out["k64"])
+        assert np.array_equal(out["k32"], out["k64"]) and np.array_equal(out["k32"], out["stubs"])
 
 
 def test_build_vs_faithful_reference_order(orc):
@@ -492,6 +492,31 @@ def test_graph_replay_equals_plain_launches(orc):
         a.simple_sim(1e-3, 5)            # graph reused
         b.simple_sim(1e-3, 2); b.simple_sim(1e-3, 2); b.simple_sim(1e-3, 1)
         assert a.download().tobytes() == b.download().tobytes()
+
+
+@pytest.mark.parametrize("kind", ["two_scales", "pairs"])
+def test_graph_replay_with_64_bit_sort_fallback(orc, kind):
+    """Inside a replayed step the 64-bit sort passes sit in a conditional graph node; inputs that need them (and
+    inputs that only need the fix-up) must give the plain-launch trajectory bit for bit, and the oracle's within 1e-12."""
+    parts = _clustered(20000, seed=3, kind=kind)
+    parts["v"] *= 1e-6                   # the tight cluster stays tight: every step needs the same sort path
+    parts["m"] *= 1e-20                  # ... and close pairs do not blow the trajectory up
+    with kd.KDTreeSim() as a, kd.KDTreeSim() as b:
+        a.upload(parts)
+        b.upload(parts)
+        a.simple_sim(1e-4, 6)            # 1 plain step + 5 graph replays
+        for _ in range(3):
+            b.simple_sim(1e-4, 2)        # plain launches only (host decides about the 64-bit passes)
+        ga, gb = a.download(), b.download()
+        assert ga.tobytes() == gb.tobytes()
+        a.build_tree()
+        gnodes, gidx = a.tree()
+    o = parts.copy()
+    orc.simple_sim(o, 1e-4, 6, order=ORDER_CANONICAL)
+    scale = np.abs(o["p"]).max()
+    assert np.abs(ga["p"] - o["p"]).max() / scale <= 1e-12
+    onodes, oidx, _ = orc.build_tree_canonical(ga, threads=4)
+    assert_tree_bit_exact(orc, gnodes, gidx, onodes, oidx, 8)
 
 
 def test_kdtree_sim_cli(orc):
