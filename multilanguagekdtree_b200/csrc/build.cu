@@ -16,6 +16,8 @@
 //    leaves, the tree-ordered particle copies and sums m / sum(m*p) bottom-up inside the segment;
 //  * a last single-CTA kernel carries m / sum(m*p) up the few global levels.
 // m and cm are summed in the canonical order (leaf: ascending id, internal: left + right), see DESIGN.md.
+#include <cstdlib>
+
 #include "ctx.cuh"
 
 namespace kdnb {
@@ -29,11 +31,18 @@ struct Pos3c {
 
 // ------------------------------------------------------------------------------------------ global levels
 
-__global__ void build_root(uint32_t* tstart, uint32_t* tlen, uint32_t* tnode, uint32_t n) {
+// lvl_ctl (device): [0..63] per-level CTA tickets, [64] build epoch, [65] look-back timeout flag
+constexpr int LC_EPOCH = 64, LC_ERR = 65, LC_WORDS = 72;
+
+__global__ void build_root(uint32_t* tstart, uint32_t* tlen, uint32_t* tnode, uint32_t n, uint32_t* lvl_ctl) {
   pdl_sync();
-  tstart[0] = 0;
-  tlen[0] = n;
-  tnode[0] = 0;
+  if (threadIdx.x == 0) {
+    tstart[0] = 0;
+    tlen[0] = n;
+    tnode[0] = 0;
+    lvl_ctl[LC_EPOCH] += 1u;
+  }
+  if (threadIdx.x < 64) lvl_ctl[threadIdx.x] = 0u;
 }
 
 // Statistics of segment s of `level` (bbox from the list ends, split dimension, median).  Every CTA working on the
@@ -114,11 +123,12 @@ level_count(Pos3c pos, Lists L, int level, uint32_t cps, uint32_t mp, int layout
   __shared__ SegStats st;
   const uint32_t seg = blockIdx.x / cps, chunk = blockIdx.x % cps, e = blockIdx.y;
   const uint32_t nseg = 1u << level;
+  if (flat[e]) return;  // (dimension 0 is never flat: its chunk-0 CTA is the writer)
   if (threadIdx.x == 0)
     st = seg_stats(pos, L, level, seg, mp, layout, tstart, tlen, tnode, tmid, tsd, nodes, flat, rk, n, tmr,
                    chunk == 0 && e == 0);
   __syncthreads();
-  if (st.sd == e || flat[e]) return;  // the split-dimension list is already partitioned; flat lists are unused
+  if (st.sd == e) return;  // the split-dimension list is already partitioned
   const uint32_t a = st.a, len = st.len, rmid = st.rmid;
   const uint32_t* lst = L.l[e];
   const uint32_t* rks = rk + (uint64_t)st.sd * n;
@@ -141,7 +151,7 @@ level_count(Pos3c pos, Lists L, int level, uint32_t cps, uint32_t mp, int layout
 }
 
 // stable partition of list e inside each segment (copy for the split-dimension list)
-__global__ void __launch_bounds__(LVL_THREADS) level_scatter(Lists Lin, Lists Lout, int level, uint32_t cps,
+__global__ void __launch_bounds__(LVL_THREADS, 8) level_scatter(Lists Lin, Lists Lout, int level, uint32_t cps,
                                                              const uint32_t* __restrict__ tstart,
                                                              const uint32_t* __restrict__ tlen,
                                                              const uint32_t* __restrict__ tmid,
@@ -213,6 +223,137 @@ __global__ void __launch_bounds__(LVL_THREADS) level_scatter(Lists Lin, Lists Lo
       uint32_t lrank = leftbase + pre + __popc(bl[k] & lt);  // lefts before me in the segment
       bool isleft = (bl[k] >> lane) & 1u;
       uint32_t dst = isleft ? a + lrank : mid + (o - lrank);
+      lout[dst] = id[k];
+    }
+    pre += __popc(bl[k]);
+  }
+}
+
+// ---- one kernel per global level: stable partition of every list inside every segment, single pass.
+// A CTA owns one chunk (LVL_CHUNK entries) of one segment of one list.  It takes a ticket (CTAs are numbered in the
+// order they START, so a CTA only ever waits for CTAs that are already running), evaluates the segment statistics,
+// flags its entries (left = initial rank along the split dimension below the median's), and obtains the number of
+// lefts in the earlier chunks of its segment by decoupled look-back over per-chunk status words
+//     epoch (30 bits) | state (2 bits: 1 = chunk count, 2 = inclusive prefix) | value (32 bits)
+// written and polled as single 64-bit words.  The epoch (build counter * 64 + level + 1) makes stale words of earlier
+// launches unreadable, so the array is never cleared.  This replaces the count + scatter kernel pair (which read the
+// lists and gathered the ranks twice and paid two launch latencies per level).
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(LVL_THREADS)
+level_partition(Pos3c pos, Lists Lin, Lists Lout, int level, uint32_t cps, uint32_t mp, int layout,
+                uint32_t* __restrict__ tstart, uint32_t* __restrict__ tlen, uint32_t* __restrict__ tnode,
+                uint32_t* __restrict__ tmid, uint8_t* __restrict__ tsd, WNode* __restrict__ nodes,
+                const uint32_t* __restrict__ rk, uint32_t n, uint32_t* __restrict__ tmr,
+                unsigned long long* __restrict__ status, uint32_t* __restrict__ lvl_ctl,
+                const uint32_t* __restrict__ flat) {
+  pdl_sync();
+  constexpr int IPT = LVL_CHUNK / LVL_THREADS;  // 8
+  __shared__ uint32_t wtot[LVL_THREADS / 32];
+  __shared__ SegStats st;
+  __shared__ uint32_t s_ticket, s_leftbase;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&lvl_ctl[level], 1u);
+  __syncthreads();
+  const uint32_t nseg = 1u << level, off = nseg - 1, gx = nseg * cps;
+  const uint32_t e = s_ticket / gx, bx = s_ticket % gx;
+  const uint32_t seg = bx / cps, chunk = bx % cps;
+  if (flat[e]) return;  // (dimension 0 is never flat: its chunk-0 CTA is the writer)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  if (threadIdx.x == 0)
+    st = seg_stats(pos, Lin, level, seg, mp, layout, tstart, tlen, tnode, tmid, tsd, nodes, flat, rk, n, tmr,
+                   chunk == 0 && e == 0);
+  // the entries of this chunk are loaded while thread 0 walks the dependent loads of the statistics
+  const uint32_t a = tstart[off + seg], len = tlen[off + seg];
+  const uint32_t* lin = Lin.l[e];
+  uint32_t* lout = Lout.l[e];
+  const uint32_t wbase_off = chunk * LVL_CHUNK + w * (32 * IPT);
+  uint32_t id[IPT];
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const uint32_t o = wbase_off + k * 32 + lane;
+    id[k] = o < len ? lin[a + o] : 0u;
+  }
+  __syncthreads();
+  if (st.sd == e) {  // the split-dimension list is already partitioned: copy
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const uint32_t o = wbase_off + k * 32 + lane;
+      if (o < len) lout[a + o] = id[k];
+    }
+    return;
+  }
+  const uint32_t* rks = rk + (uint64_t)st.sd * n;
+  const uint32_t rmid = st.rmid, mid = st.mid;
+  uint32_t bl[IPT];
+  uint32_t wl = 0;
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const uint32_t o = wbase_off + k * 32 + lane;
+    const bool isleft = o < len && (rks[id[k]] < rmid);
+    bl[k] = __ballot_sync(0xffffffffu, isleft);
+    wl += __popc(bl[k]);
+  }
+  if (lane == 0) wtot[w] = wl;
+  __syncthreads();
+  uint32_t wbase = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < LVL_THREADS / 32; ++k) {
+    if (k < w) wbase += wtot[k];
+    total += wtot[k];
+  }
+  if (w == 0) {  // publish this chunk's count, look back for the lefts of the earlier chunks, publish the prefix
+    const unsigned long long epoch = ((unsigned long long)((lvl_ctl[LC_EPOCH] << 6) + (uint32_t)level + 1u) & 0x3fffffffull) << 34;
+    unsigned long long* row = status + ((uint64_t)e * nseg + seg) * cps;
+    uint32_t excl = 0;
+    if (chunk > 0) {
+      if (lane == 0) st_status(&row[chunk], epoch | (1ull << 32) | total);
+      int j = (int)chunk - 1;
+      uint32_t polls = 0;
+      for (;;) {
+        const int idx = j - lane;
+        unsigned long long v = epoch | (2ull << 32);  // before chunk 0: an inclusive prefix of 0
+        if (idx >= 0) v = ld_status(&row[idx]);
+        const uint32_t state = ((v >> 34) == (epoch >> 34)) ? (uint32_t)(v >> 32) & 3u : 0u;
+        const uint32_t have = __ballot_sync(0xffffffffu, state != 0u);
+        const uint32_t incl = __ballot_sync(0xffffffffu, state == 2u);
+        const int first = incl ? __ffs(incl) - 1 : 32;                      // nearest inclusive prefix in this window
+        const uint32_t need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);  // lanes 0..first
+        if ((have & need) == need) {
+          uint32_t val = (lane <= first) ? (uint32_t)v : 0u;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+          excl += val;
+          if (first < 32) break;
+          j -= 32;
+        } else if (++polls > (1u << 22)) {  // a predecessor never published (cannot happen): do not hang the GPU
+          if (lane == 0) lvl_ctl[LC_ERR] = 1u;
+          break;
+        }
+      }
+    }
+    if (lane == 0) {
+      st_status(&row[chunk], epoch | (2ull << 32) | (unsigned long long)(excl + total));
+      s_leftbase = excl;
+    }
+  }
+  __syncthreads();
+  const uint32_t leftbase = s_leftbase;
+  uint32_t pre = wbase;
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const uint32_t o = wbase_off + k * 32 + lane;
+    if (o < len) {
+      const uint32_t lrank = leftbase + pre + __popc(bl[k] & lt);  // lefts before me in the segment
+      const bool isleft = (bl[k] >> lane) & 1u;
+      const uint32_t dst = isleft ? a + lrank : mid + (o - lrank);
       lout[dst] = id[k];
     }
     pre += __popc(bl[k]);
@@ -552,7 +693,8 @@ int build_tree(Ctx* c) {
     g_bottom_attr_set = true;
   }
   Pos3c pos = {{c->pos[0], c->pos[1], c->pos[2]}};
-  KDNB_LAUNCH(c, build_root, 1, 1, 0, c->tstart, c->tlen, c->tnode, n);
+  KDNB_LAUNCH(c, build_root, 1, 64, 0, c->tstart, c->tlen, c->tnode, n, c->lvl_ctl);
+  static const bool split_kernels = getenv("KDNB_LEVEL_SPLIT") != nullptr;  // profiling knob: count + scatter kernel pair
   int cur = 0;
   for (int lev = 0; lev < c->l0; ++lev) {
     const uint32_t nseg = 1u << lev;
@@ -560,10 +702,16 @@ int build_tree(Ctx* c) {
     const uint32_t cps = (maxlen + LVL_CHUNK - 1) / LVL_CHUNK;
     Lists Lin = {{c->list[cur], c->list[cur] + n, c->list[cur] + 2ull * n}};
     Lists Lout = {{c->list[cur ^ 1], c->list[cur ^ 1] + n, c->list[cur ^ 1] + 2ull * n}};
-    KDNB_LAUNCH(c, level_count, dim3(nseg * cps, 3), LVL_THREADS, 0, pos, Lin, lev, cps, c->mp, c->layout, c->tstart,
-                c->tlen, c->tnode, c->tmid, c->tsd, c->nodes, c->rk, n, c->tmr, c->chunk_cnt, c->flat);
-    KDNB_LAUNCH(c, level_scatter, dim3(nseg * cps, 3), LVL_THREADS, 0, Lin, Lout, lev, cps, c->tstart, c->tlen,
-                c->tmid, c->tsd, c->rk, n, c->tmr, c->chunk_cnt, c->flat);
+    if (split_kernels) {
+      KDNB_LAUNCH(c, level_count, dim3(nseg * cps, 3), LVL_THREADS, 0, pos, Lin, lev, cps, c->mp, c->layout, c->tstart,
+                  c->tlen, c->tnode, c->tmid, c->tsd, c->nodes, c->rk, n, c->tmr, c->chunk_cnt, c->flat);
+      KDNB_LAUNCH(c, level_scatter, dim3(nseg * cps, 3), LVL_THREADS, 0, Lin, Lout, lev, cps, c->tstart, c->tlen,
+                  c->tmid, c->tsd, c->rk, n, c->tmr, c->chunk_cnt, c->flat);
+    } else {
+      KDNB_LAUNCH(c, level_partition, nseg * cps * 3, LVL_THREADS, 0, pos, Lin, Lout, lev, cps, c->mp, c->layout,
+                  c->tstart, c->tlen, c->tnode, c->tmid, c->tsd, c->nodes, c->rk, n, c->tmr,
+                  reinterpret_cast<unsigned long long*>(c->lvl_status), c->lvl_ctl, c->flat);
+    }
     cur ^= 1;
   }
   Lists Lb = {{c->list[cur], c->list[cur] + n, c->list[cur] + 2ull * n}};

@@ -71,6 +71,8 @@ struct Ctx {
   uint8_t* tsd = nullptr;
   uint32_t* inv = nullptr;                 // [n] id -> local slot inside a bottom segment
   uint32_t* chunk_cnt = nullptr;           // [3][nseg][chunks] left counts per chunk
+  uint64_t* lvl_status = nullptr;          // [3][nseg][chunks] look-back status words of level_partition (build.cu)
+  uint32_t* lvl_ctl = nullptr;             // [72] per-level tickets, build epoch, timeout flag
   uint64_t table_cap = 0, chunk_cap = 0;
 
   // tree + tree-ordered views

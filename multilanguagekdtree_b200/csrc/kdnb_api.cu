@@ -114,6 +114,8 @@ static void free_all(Ctx* c) {
   fr(c->tmid);
   fr(c->tsd);
   fr(c->chunk_cnt);
+  fr(c->lvl_status);
+  fr(c->lvl_ctl);
   fr(c->nodes);
   fr(c->ms);
   fr(c->perm);
@@ -273,6 +275,10 @@ static int plan(Ctx* c, uint64_t n) {
     if (!rc) rc = dev_alloc(c, &c->tmid, table);
     if (!rc) rc = dev_alloc(c, &c->tsd, table);
     if (!rc) rc = dev_alloc(c, &c->chunk_cnt, chunks);
+    if (!rc) rc = dev_alloc(c, &c->lvl_status, chunks);
+    if (!rc) rc = dev_alloc(c, &c->lvl_ctl, 72);
+    if (!rc) KDNB_CUDA_TRY(c, cudaMemsetAsync(c->lvl_status, 0, chunks * sizeof(uint64_t), c->stream));
+    if (!rc) KDNB_CUDA_TRY(c, cudaMemsetAsync(c->lvl_ctl, 0, 72 * sizeof(uint32_t), c->stream));
     if (!rc) rc = dev_alloc(c, &c->nodes, c->n_nodes + (n + 1) / 2 + 1);  // node records, then the tree-ordered particles (one pool: walk.cu)
     if (!rc) rc = dev_alloc(c, &c->ms, c->n_nodes);
     if (!rc) rc = dev_alloc(c, &c->perm, n);

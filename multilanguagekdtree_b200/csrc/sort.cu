@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) sort_scan_rows(uint32_t* __restrict__ his
 
 // ---- pass kernel 3: stable rank inside the tile (warp match), scatter
 template <bool FIRST, bool LAST, typename K>
-__global__ void __launch_bounds__(SORT_THREADS) sort_downsweep(Pos3 pos, const K* __restrict__ keys_in,
+__global__ void __launch_bounds__(SORT_THREADS, 8) sort_downsweep(Pos3 pos, const K* __restrict__ keys_in,
                                                                const uint32_t* __restrict__ vals_in,
                                                                K* __restrict__ keys_out,
                                                                uint32_t* __restrict__ vals_out, uint32_t n,
