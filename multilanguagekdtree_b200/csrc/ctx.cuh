@@ -104,6 +104,8 @@ struct Ctx {
   uint64_t graph_n = 0, graph_launches = 0;
   double graph_dt = 0.0;
   int graph_world = 0;
+  uint64_t seen_n = 0, seen_calls = 0;  // consecutive kdnb_simple_sim calls with the same (n, dt)
+  double seen_dt = 0.0;
 
   // measurement
   uint64_t launches = 0;
