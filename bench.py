@@ -290,8 +290,8 @@ def run_kdnb(args) -> None:
                 "kernel": "walk2_kernel", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if fp64_peak else None,
                 # DRAM bytes of one launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu capture
-                # profiles/r01_launches_*.csv; measured at N=1M on one GPU only
-                "traffic": 56.5e6 if (n == 1_000_000 and world == 1) else None,
+                # profiles/r01_walk_kernel_ncu_full_raw.csv (53.0 MB read + 7.1 MB written); measured at N=1M on one GPU only
+                "traffic": 60.2e6 if (n == 1_000_000 and world == 1) else None,
                 "peak_source": "DFMA-chain microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)",
                 "flops_per_particle_step": flops_step / (n + 1),
                 "counts_per_particle": {"node_tests": V / (n + 1), "accepts": A / (n + 1), "leaf_visits": LV / (n + 1), "pairs": P / (n + 1)},
