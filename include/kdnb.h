@@ -120,6 +120,16 @@ int kdnb_download_tree(kdnb_ctx* ctx, kdnb_node* nodes, uint64_t cap, uint64_t* 
 /* per particle {internal nodes tested, monopoles accepted, leaves visited, pair interactions}; needs KDNB_FLAG_WALK_COUNTS */
 int kdnb_download_walk_counts(kdnb_ctx* ctx, uint64_t* counts /* count*4, original order */);
 
+/* ---- quickstat_index (Parallel/RustVersion/src/quickstat.rs:9-34; stand-alone bench src/bin/bench_quickstat.rs).
+ * Permutes indices[0..count) (element ids into vals[0..n_vals)) so that indices[goal] refers to the goal-th smallest
+ * value, nothing before it is larger and nothing after it is smaller (the post-condition of quickstat.rs:199-253).
+ * Device radix select + one stable three-way partition: of the permutations the reference's random pivots can
+ * produce, the one that keeps the input order inside {< pivot}, {== pivot}, {> pivot}.  Host arrays in, host arrays
+ * out; *device_ms (may be NULL) receives the device time of the selection without the copies.
+ * Where the reference would panic (goal >= count, an index >= n_vals) a negative code is returned. */
+int kdnb_quickstat_index(kdnb_ctx* ctx, const double* vals, uint64_t n_vals, uint64_t* indices, uint64_t count,
+                         uint64_t goal, double* device_ms);
+
 /* ---- pure functions */
 uint64_t kdnb_nodes_needed(uint64_t num_parts, uint32_t max_parts); /* nodes_needed_for_particles (array_kd_tree.rs:45-53) */
 uint64_t kdnb_node_count(const kdnb_ctx* ctx); /* allocate_node_vec(count).len() for this context's layout (array_kd_tree.rs:55-60) */

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkdnb.so")
 CLI = os.path.join(HERE, "kdtree-sim")
-CU = ["kdnb_api.cu", "sort.cu", "build.cu", "walk.cu", "kick.cu", "peak.cu"]
+CU = ["kdnb_api.cu", "sort.cu", "build.cu", "walk.cu", "kick.cu", "select.cu", "peak.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
@@ -32,7 +32,7 @@ def _newer(target: str, sources: list[str]) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, f) for f in CU]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("common.cuh", "ctx.cuh")] + [os.path.join(HERE, "..", "include", "kdnb.h")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("common.cuh", "ctx.cuh", "walk2.cuh", "walk_legacy.cuh")] + [os.path.join(HERE, "..", "include", "kdnb.h")]
     if force or not _newer(LIB, deps):
         cmd = [nvcc, *NVCC_FLAGS, "-shared", "-o", LIB, *srcs, "-ldl"]
         if verbose:

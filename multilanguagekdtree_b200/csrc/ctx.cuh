@@ -137,6 +137,9 @@ int soa_to_aos(Ctx* c);
 int gather_acc(Ctx* c, double* dst_orig_order);
 int scatter_acc(Ctx* c, const double* src_orig_order);
 int gather_counts(Ctx* c, unsigned long long* dst_orig_order);
+// select.cu
+int select_run(Ctx* c, const double* d_vals, const uint64_t* d_idx64, uint64_t count, uint64_t goal, uint64_t* d_keys,
+               uint32_t* d_idx32, uint2* d_tiles, uint64_t* d_state, uint64_t* d_out64);
 // peak.cu
 int measure_fp64_peak(Ctx* c, double* tflops);
 

@@ -740,6 +740,55 @@ int kdnb_stage_reset(kdnb_ctx* ctx) {
 
 uint64_t kdnb_launch_count(const kdnb_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
 
+int kdnb_quickstat_index(kdnb_ctx* ctx, const double* vals, uint64_t n_vals, uint64_t* indices, uint64_t count,
+                         uint64_t goal, double* device_ms) {
+  CTX_OR_FAIL(ctx);
+  if (!vals || !indices) return c->fail(KDNB_E_INVALID, "null array");
+  if (count == 0 || goal >= count) return c->fail(KDNB_E_INVALID, "goal out of range");  // the reference indexes out of bounds
+  if (n_vals == 0 || n_vals > 0xffffffffull || count > 0xffffff00ull)
+    return c->fail(KDNB_E_INVALID, "value count exceeds the 32-bit index range of the device path");
+  for (uint64_t i = 0; i < count; ++i)
+    if (indices[i] >= n_vals) return c->fail(KDNB_E_INVALID, "index out of range of vals");
+  KDNB_CUDA_TRY(c, cudaSetDevice(c->device));
+  const uint64_t ntiles = (count + 2047) / 2048;
+  double* d_vals = nullptr;
+  uint64_t *d_idx = nullptr, *d_keys = nullptr, *d_state = nullptr;
+  uint32_t* d_idx32 = nullptr;
+  uint2* d_tiles = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_vals), cudaFree(d_idx), cudaFree(d_keys), cudaFree(d_state), cudaFree(d_idx32), cudaFree(d_tiles);
+  };
+  cudaError_t e = cudaSuccess;
+  if ((e = cudaMalloc(&d_vals, n_vals * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(&d_idx, count * sizeof(uint64_t))) != cudaSuccess ||
+      (e = cudaMalloc(&d_keys, count * sizeof(uint64_t))) != cudaSuccess ||
+      (e = cudaMalloc(&d_state, 8 * sizeof(uint64_t) + 256 * sizeof(uint32_t))) != cudaSuccess ||
+      (e = cudaMalloc(&d_idx32, count * sizeof(uint32_t))) != cudaSuccess ||
+      (e = cudaMalloc(&d_tiles, ntiles * sizeof(uint2))) != cudaSuccess) {
+    cleanup();
+    return c->fail(KDNB_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  int rc = 0;
+  float ms = 0.f;
+  if ((e = cudaMemcpyAsync(d_vals, vals, n_vals * sizeof(double), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(d_idx, indices, count * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) {
+    rc = c->fail(KDNB_E_CUDA, std::string("upload: ") + cudaGetErrorString(e));
+  }
+  if (!rc) {
+    cudaEventRecord(c->sw_begin, c->stream);
+    // (the u64 index buffer is dead once sel_keys has narrowed it to u32: it receives the result)
+    rc = select_run(c, d_vals, d_idx, count, goal, d_keys, d_idx32, d_tiles, d_state, d_idx);
+    cudaEventRecord(c->sw_end, c->stream);
+  }
+  if (!rc && (e = cudaMemcpyAsync(indices, d_idx, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess)
+    rc = c->fail(KDNB_E_CUDA, std::string("download: ") + cudaGetErrorString(e));
+  if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess && !rc)
+    rc = c->fail(KDNB_E_CUDA, std::string("select: ") + cudaGetErrorString(e));
+  if (!rc && device_ms && cudaEventElapsedTime(&ms, c->sw_begin, c->sw_end) == cudaSuccess) *device_ms = ms;
+  cleanup();
+  return rc;
+}
+
 int kdnb_measure_fp64_peak(kdnb_ctx* ctx, double* tflops_out) {
   CTX_OR_FAIL(ctx);
   if (!tflops_out) return c->fail(KDNB_E_INVALID, "null output");

@@ -519,6 +519,63 @@ def test_graph_replay_with_64_bit_sort_fallback(orc, kind):
     assert_tree_bit_exact(orc, gnodes, gidx, onodes, oidx, 8)
 
 
+def test_quickstat_small_test_kat_gpu():
+    """quickstat.rs:191-197 (the reference's one known-answer test) through kdnb_quickstat_index."""
+    vals = np.array([2.3, 9.8, 3.1, 1.6, 6.7, 7.8, 8.6])
+    idx = np.arange(7, dtype=np.uint64)
+    kd.quickstat_index(idx, 3, vals)
+    assert idx[3] == 4
+    assert sorted(idx.tolist()) == list(range(7))
+
+
+def test_quickstat_random_and_slices_gpu(orc):
+    """quickstat.rs:199-253: `<` left of goal, `>=` right of it, entries outside the slice untouched; plus, beyond the
+    reference's tests, the selected element is THE goal-th order statistic (numpy) and the oracle's quick-select
+    agrees on it."""
+    rng = np.random.default_rng(17)
+    n = 100000
+    with kd.KDTreeSim() as sim:
+        for trial in range(6):
+            vals = rng.random(n)
+            idx = np.arange(n, dtype=np.uint64)
+            start = int(rng.integers(0, n // 4)) if trial else 0
+            end = start + int(rng.integers(1, 3 * n // 4)) if trial else n
+            goal = int(rng.integers(start, end))
+            sl = idx[start:end]                       # a view: permuted in place like `&mut indices[start..end]`
+            tmp = np.ascontiguousarray(sl)
+            kd.quickstat_index(tmp, goal - start, vals, sim=sim)
+            sl[:] = tmp
+            pivot = vals[idx[goal]]
+            assert np.all(vals[idx[start:goal]] < pivot) and np.all(vals[idx[goal:end]] >= pivot)
+            assert np.array_equal(idx[:start], np.arange(start, dtype=np.uint64))
+            assert np.array_equal(idx[end:], np.arange(end, n, dtype=np.uint64))
+            assert np.array_equal(np.sort(idx[start:end]), np.arange(start, end, dtype=np.uint64))
+            assert pivot == np.partition(vals[start:end], goal - start)[goal - start]
+            oidx = np.arange(start, end, dtype=np.uint64)
+            orc.quickstat_index(oidx, goal - start, vals, seed=trial + 1)
+            assert vals[oidx[goal - start]] == pivot
+
+
+def test_quickstat_duplicates_signs_and_errors_gpu():
+    """Ties, negative values and -0.0: the three blocks keep the input order (canonical permutation); panics of the
+    reference (goal out of range, index out of range) become error codes."""
+    rng = np.random.default_rng(5)
+    vals = np.round(rng.normal(size=50000) * 4.0) / 4.0          # heavy duplicates, both signs
+    vals[::97] = -0.0
+    idx = rng.permutation(len(vals)).astype(np.uint64)
+    before = idx.copy()
+    goal = 23456
+    kd.quickstat_index(idx, goal, vals)
+    pivot = vals[idx[goal]]
+    assert pivot == np.sort(vals)[goal]
+    less, equal, greater = before[vals[before] < pivot], before[vals[before] == pivot], before[vals[before] > pivot]
+    assert np.array_equal(idx, np.concatenate([less, equal, greater]))       # stable three-way partition
+    with pytest.raises(kd.KdnbError):
+        kd.quickstat_index(np.arange(10, dtype=np.uint64), 10, np.zeros(10))
+    with pytest.raises(kd.KdnbError):
+        kd.quickstat_index(np.array([0, 1, 99], dtype=np.uint64), 1, np.zeros(10))
+
+
 def test_kdtree_sim_cli(orc):
     """The C++ driver mirrors Parallel/RustVersion/src/main.rs: --number/-n required, --steps/-s default 1, prints seconds."""
     import os
@@ -533,3 +590,8 @@ def test_kdtree_sim_cli(orc):
     assert r.returncode == 0 and "walk=" in r.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=30)
     assert r.returncode == 2 and "--number" in r.stderr
+    # positional form of the reference's other CLIs (Parallel/CppVersion/kdtree-sim.cpp:14-16): steps n threads
+    r = subprocess.run([exe, "3", "20000", "8"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and float(r.stdout.strip()) > 0.0, r.stderr
+    r = subprocess.run([exe, "3"], capture_output=True, text=True, timeout=30)
+    assert r.returncode == 1
