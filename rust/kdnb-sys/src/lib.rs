@@ -87,6 +87,7 @@ extern "C" {
     pub fn kdnb_stage_ms(ctx: *mut kdnb_ctx, ms_out: *mut c_double, steps_out: *mut u64) -> c_int;
     pub fn kdnb_stage_reset(ctx: *mut kdnb_ctx) -> c_int;
     pub fn kdnb_launch_count(ctx: *const kdnb_ctx) -> u64;
+    pub fn kdnb_quickstat_index(ctx: *mut kdnb_ctx, vals: *const c_double, n_vals: u64, indices: *mut u64, count: u64, goal: u64, device_ms: *mut c_double) -> c_int;
     pub fn kdnb_measure_fp64_peak(ctx: *mut kdnb_ctx, tflops_out: *mut c_double) -> c_int;
     pub fn kdnb_flush_l2(ctx: *mut kdnb_ctx) -> c_int;
     pub fn kdnb_device_ms(ctx: *mut kdnb_ctx, begin_or_end: c_int, ms_out: *mut c_double) -> c_int;
