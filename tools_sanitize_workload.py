@@ -11,4 +11,23 @@ for n, mp, layout in ((5000, 8, kd.LAYOUT_PADDED), (3000, 7, kd.LAYOUT_DENSE), (
     with kd.KDTreeSim(max_parts=mp, layout=layout) as sim:
         sim.simple_sim_bodies(parts, 1e-3, 4)
     assert np.isfinite(out["p"]).all()
+# inputs beyond the 32-bit sort keys: fix-up of equal-key runs, 64-bit fallback (plain launches and conditional graph node)
+rng = np.random.default_rng(7)
+for kind in ("cluster", "pairs"):
+    parts = kd.circular_orbits(20000, seed=3)
+    parts["m"] *= 1e-6
+    if kind == "cluster":
+        parts["p"][: 10000, :2] = 0.25 + rng.random((10000, 2)) * 1e-8
+    else:
+        base = np.sort(rng.random(10000) * 2.0 - 1.0)
+        parts["p"][1::2, 0][:10000] = np.nextafter(base, 2.0)
+        parts["p"][2::2, 0][:10000] = base
+    with kd.KDTreeSim() as sim:
+        sim.upload(parts); sim.build_tree(); sim.calc_accel(); sim.simple_sim(1e-5, 5); out = sim.download()
+    assert np.isfinite(out["p"]).all()
+# stand-alone quickstat_index
+vals = rng.random(300000)
+idx = np.arange(len(vals), dtype=np.uint64)
+kd.quickstat_index(idx, 123456, vals)
+assert vals[idx[123456]] == np.sort(vals)[123456]
 print("sanitizer workload done")
