@@ -1,5 +1,5 @@
 // walk_model.c — development aid (NOT product, NOT test): replays the warp-level traversal schedule of
-// csrc/walk.cu on the CPU over the oracle's canonical tree and counts the events that set its instruction count
+// csrc/walk2.cuh on the CPU over the oracle's canonical tree and counts the events that set its instruction count
 // (pop batches and their fill, far / near / mixed / leaf nodes, deferred rounds, list entries and their mask
 // population).  Used to size queues and to predict the effect of schedule changes without GPU time.
 #include <math.h>
@@ -8,7 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "../oracle/kdtree_oracle.h"
+#include "../../oracle/kdtree_oracle.h"
 
 typedef struct {
   double batches, popped, farn, nearn, mixed, leaves, entries, lanes, mixed_rounds, mixed_round_nodes, leaf_rounds,

@@ -1,7 +1,7 @@
-"""Development aid: event counts of the walk schedule on the CPU (see walk_model.c).  Usage: python tools/walk_model.py [N] [groups]"""
+"""Development aid: event counts of the walk schedule on the CPU (see walk_model.c).  Usage: python tests/devtools/walk_model.py [N] [groups]"""
 import ctypes as C, os, subprocess, sys
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 from oracle import okd
 
 here = os.path.dirname(os.path.abspath(__file__))
