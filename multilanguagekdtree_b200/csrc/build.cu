@@ -564,30 +564,20 @@ build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_
     cur ^= 1;
   }
 
-  // ---- leaves.  (1) one thread per leaf puts its slots in ascending particle-id order (canonical leaf order);
+  // ---- leaves.  (1) one thread per SLOT finds its place in the ascending particle-id order of its leaf (canonical
+  //          leaf order) by counting the smaller ids among the <= MAX_PARTS members;
   //      (2) one thread per SLOT gathers {x,y,z,m} (one sector of the AoS copy, all gathers of the CTA in flight
   //          together) and writes perm / rank / posm coalesced;
   //      (3) one thread per leaf sums m and m*p sequentially in that order (array_kd_tree.rs:534-539 order of ops).
   const uint32_t hend = 2u << depth;
   uint16_t* order = S.lst[cur ^ 1][0];  // free buffer: tree slot (local) -> local id
-  for (uint32_t h = 1 + tid; h < hend; h += BOT_THREADS) {
-    BotTab t = S.tab[h];
-    if (t.kind != 1) continue;
-    uint32_t g[32];
-    uint16_t ls[32];
-    for (uint32_t k = 0; k < t.len; ++k) {
-      const uint16_t l = S.lst[cur][0][t.a + k];
-      const uint32_t v = S.gid[l];
-      int j = (int)k - 1;
-      while (j >= 0 && g[j] > v) {
-        g[j + 1] = g[j];
-        ls[j + 1] = ls[j];
-        --j;
-      }
-      g[j + 1] = v;
-      ls[j + 1] = l;
-    }
-    for (uint32_t k = 0; k < t.len; ++k) order[t.a + k] = ls[k];
+  for (uint32_t p = tid; p < len0; p += BOT_THREADS) {
+    const BotTab t = S.tab[S.segh[p]];  // the leaf that holds slot p
+    const uint16_t l = S.lst[cur][0][p];
+    const uint32_t v = S.gid[l];
+    uint32_t r = 0;
+    for (uint32_t k = 0; k < t.len; ++k) r += S.gid[S.lst[cur][0][t.a + k]] < v;
+    order[t.a + r] = l;
   }
   __syncthreads();
   for (uint32_t p = tid; p < len0; p += BOT_THREADS) {
@@ -598,6 +588,10 @@ build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_
     posm[a0 + p] = q;
   }
   __syncthreads();
+  // {M, sum m*x, sum m*y, sum m*z} of the nodes of this segment live in shared memory (over the id / list buffers,
+  // dead from here on); only the segment root's goes to global memory, for build_topup
+  static_assert(sizeof(S.gid) + sizeof(S.lst) >= 1024 * 4 * sizeof(double), "node sums alias gid + lst (heap <= 1024)");
+  double* msl = reinterpret_cast<double*>(smem_raw);
   for (uint32_t h = 1 + tid; h < hend; h += BOT_THREADS) {
     BotTab t = S.tab[h];
     if (t.kind != 1) continue;
@@ -610,7 +604,8 @@ build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_
       sy = __dadd_rn(sy, __dmul_rn(q.m, q.y));
       sz = __dadd_rn(sz, __dmul_rn(q.m, q.z));
     }
-    ms[t.node] = make_double4(m, sx, sy, sz);
+    msl[4 * h + 0] = m, msl[4 * h + 1] = sx, msl[4 * h + 2] = sy, msl[4 * h + 3] = sz;
+    if (h == 1) ms[t.node] = make_double4(m, sx, sy, sz);
     WNode* nd = &nodes[t.node];
     nd->cx = sx;  // not part of the reference's Leaf; kept for debugging only
     nd->cy = sy;
@@ -629,9 +624,10 @@ build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_
     for (uint32_t h = nn + tid; h < 2 * nn; h += BOT_THREADS) {
       BotTab t = S.tab[h];
       if (t.kind != 0) continue;
-      const double4 l = ms[S.tab[2 * h].node], r = ms[S.tab[2 * h + 1].node];
-      double4 s = make_double4(__dadd_rn(l.x, r.x), __dadd_rn(l.y, r.y), __dadd_rn(l.z, r.z), __dadd_rn(l.w, r.w));
-      ms[t.node] = s;
+      const double* l = msl + 8 * h;  // children 2h and 2h + 1
+      const double4 s = make_double4(__dadd_rn(l[0], l[4]), __dadd_rn(l[1], l[5]), __dadd_rn(l[2], l[6]), __dadd_rn(l[3], l[7]));
+      msl[4 * h + 0] = s.x, msl[4 * h + 1] = s.y, msl[4 * h + 2] = s.z, msl[4 * h + 3] = s.w;
+      if (h == 1) ms[t.node] = s;
       WNode* nd = &nodes[t.node];
       nd->m = s.x;
       nd->cx = __ddiv_rn(s.y, s.x);
