@@ -45,7 +45,7 @@ namespace kdnb {
 
 constexpr int W2_STACK = 320;  // soft capacity: batches shrink as the stack fills
 constexpr int W2_SLACK = 32;   // depth-first tail when the stack is at capacity (tree depth <= 27 at 1e8 particles)
-constexpr int W2_LIST = 64;    // interaction-list capacity (appends come in groups of <= 32)
+constexpr int W2_LIST = 96;    // interaction-list capacity (appends come in groups of <= 32)
 
 // 1.875 = the e^2 coefficient of (1 - e)^(-3/2); read from the constant bank as an instruction operand (as a literal
 // it costs two register moves per loop iteration at the 64-register budget)
