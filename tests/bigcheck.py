@@ -21,6 +21,13 @@ with kd.KDTreeSim(flags=kd.FLAG_WALK_COUNTS) as sim:
     t0 = time.time(); sim.calc_accel(); sim.synchronize(); print("gpu walk s", time.time() - t0)
     acc = sim.accel()
     cnt = sim.walk_counts()
+with kd.KDTreeSim() as sim:                      # the production walk variant (no counters, planar shortcut)
+    sim.upload(parts)
+    sim.build_tree()
+    sim.calc_accel()
+    acc_fast = sim.accel()
+assert np.array_equal(acc_fast, acc), "production walk kernel differs from the counting variant"
+print("production walk == counting walk, bit for bit")
 assert np.array_equal(np.sort(idx), np.arange(n + 1, dtype=np.uint64))
 assert len(nodes) == orc.nodes_needed_for_particles(n + 1, 8)
 t0 = time.time(); cn, cidx, _ = orc.build_tree_canonical(parts, threads=orc.max_threads()); print("oracle build s", time.time() - t0)
