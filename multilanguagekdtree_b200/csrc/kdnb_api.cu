@@ -597,6 +597,12 @@ int kdnb_simple_sim_host(const kdnb_config* cfg, kdnb_particle* bodies, uint64_t
 int kdnb_synchronize(kdnb_ctx* ctx) {
   CTX_OR_FAIL(ctx);
   KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (c->lvl_ctl) {  // a look-back of the level partitions that gave up instead of spinning for ever (build.cu)
+    uint32_t err = 0;
+    KDNB_CUDA_TRY(c, cudaMemcpyAsync(&err, c->lvl_ctl + 65, sizeof(err), cudaMemcpyDeviceToHost, c->stream));
+    KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (err) return c->fail(KDNB_E_CUDA, "tree build: a level partition timed out waiting for a predecessor chunk");
+  }
   return 0;
 }
 

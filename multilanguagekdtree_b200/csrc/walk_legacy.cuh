@@ -1,4 +1,6 @@
-// walk_legacy.cuh — the walk kernel (device code); launched from walk.cu
+// walk_legacy.cuh — the FIRST walk kernel of round 1 (mixed nodes and leaves handled one at a time by the whole warp),
+// kept selectable for A/B timing (KDNB_WALK_CFG=1), plus the helpers walk2.cuh shares with it (Rec32, interact<>,
+// warp_min / warp_max).  The kernel that runs by default is walk2.cuh's.
 //
 // theta-criterion force walk, calc_accel / accel_recur of the reference
 // (Parallel/RustVersion/src/array_kd_tree.rs:585-621) with calc_pp_accel (array_particle.rs:67-76) in the leaves.
