@@ -11,7 +11,7 @@
 // and the children are obtained by a STABLE partition of the other two lists by "is in the left half of
 // list[split_dim]" — no selection passes, no reductions.
 //
-//  * levels whose segments are larger than BOT_CAP run as global kernels (stats, flags, count, scan, scatter);
+//  * levels whose segments are larger than BOT_CAP run as ONE global kernel each (level_partition);
 //  * once segments fit (<= BOT_CAP slots) ONE kernel finishes all remaining levels in shared memory, emits the
 //    leaves, the tree-ordered particle copies and sums m / sum(m*p) bottom-up inside the segment;
 //  * a last single-CTA kernel carries m / sum(m*p) up the few global levels.
@@ -22,8 +22,9 @@
 
 namespace kdnb {
 
+// the two ping-pong buffers of every per-dimension list: l[buffer][dimension]
 struct Lists {
-  uint32_t* l[3];
+  uint32_t* l[2][3];
 };
 struct Pos3c {
   const double* p[3];
@@ -31,15 +32,17 @@ struct Pos3c {
 
 // ------------------------------------------------------------------------------------------ global levels
 
+// Level table (device): one 16-byte record per segment, level l at offset 2^l - 1:
+//   x = first slot, y = length, z = node index, w = buffer bits (bit d set: list d of this segment lives in buffer 1).
+// The list of the split dimension is already partitioned (its first half IS the left child's list), so it stays where
+// it is; only the other lists are partitioned into the other buffer, and the children inherit the flipped bits.
 // lvl_ctl (device): [0..63] per-level CTA tickets, [64] build epoch, [65] look-back timeout flag
 constexpr int LC_EPOCH = 64, LC_ERR = 65, LC_WORDS = 72;
 
-__global__ void build_root(uint32_t* tstart, uint32_t* tlen, uint32_t* tnode, uint32_t n, uint32_t* lvl_ctl) {
+__global__ void build_root(uint4* tseg, uint32_t n, uint32_t* lvl_ctl) {
   pdl_sync();
   if (threadIdx.x == 0) {
-    tstart[0] = 0;
-    tlen[0] = n;
-    tnode[0] = 0;
+    tseg[0] = make_uint4(0u, n, 0u, 0u);  // the sort leaves every list in buffer 0
     lvl_ctl[LC_EPOCH] += 1u;
   }
   if (threadIdx.x < 64) lvl_ctl[threadIdx.x] = 0u;
@@ -49,24 +52,42 @@ __global__ void build_root(uint32_t* tstart, uint32_t* tlen, uint32_t* tnode, ui
 // segment evaluates this (a handful of gathers); the one flagged `writer` also emits the node record and the table
 // entries of the two children.  Returns sd, mid and the initial rank of the median element.
 struct SegStats {
-  uint32_t a, len, sd, mid, rmid;
+  uint32_t a, len, sd, mid, rmid, par;
 };
 __device__ __forceinline__ SegStats seg_stats(Pos3c pos, Lists L, int level, uint32_t s, uint32_t mp, int layout,
-                                              uint32_t* __restrict__ tstart, uint32_t* __restrict__ tlen,
-                                              uint32_t* __restrict__ tnode, uint32_t* __restrict__ tmid,
-                                              uint8_t* __restrict__ tsd, WNode* __restrict__ nodes,
+                                              uint4* __restrict__ tseg, WNode* __restrict__ nodes,
                                               const uint32_t* __restrict__ flat, const uint32_t* __restrict__ rk,
-                                              uint32_t n, uint32_t* __restrict__ tmr, bool writer) {
+                                              uint32_t n, bool writer) {
   const uint32_t nseg = 1u << level;
   const uint32_t off = nseg - 1;
-  const uint32_t a = tstart[off + s], len = tlen[off + s], node = tnode[off + s];
-  double mn[3], mx[3];
+  const uint4 tb = tseg[off + s];
+  const uint32_t a = tb.x, len = tb.y, node = tb.z, par = tb.w;
+  const uint32_t half = len / 2, mid = a + half;
+  // Three round trips after the table entry instead of five: the list ends AND the median entry of every dimension are
+  // fetched together, then their coordinates and the median's initial rank; the split dimension only selects among
+  // values that are already here (this chain is on the critical path of every CTA of the level).
+  uint32_t ilo[3], ihi[3], imid[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    mn[d] = mx[d] = 0.0;  // a flat dimension has extent 0 everywhere (its list is not maintained)
+    ilo[d] = ihi[d] = imid[d] = 0u;
     if (!flat[d]) {
-      mn[d] = pos.p[d][L.l[d][a]];
-      mx[d] = pos.p[d][L.l[d][a + len - 1]];
+      const uint32_t* lst = L.l[(par >> d) & 1u][d];
+      ilo[d] = lst[a];
+      ihi[d] = lst[a + len - 1];
+      imid[d] = lst[mid];
+    }
+  }
+  double mn[3], mx[3], vmid[3];
+  uint32_t rmd[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    mn[d] = mx[d] = vmid[d] = 0.0;  // a flat dimension has extent 0 everywhere (its list is not maintained)
+    rmd[d] = 0u;
+    if (!flat[d]) {
+      mn[d] = pos.p[d][ilo[d]];
+      mx[d] = pos.p[d][ihi[d]];
+      vmid[d] = pos.p[d][imid[d]];
+      rmd[d] = rk[(uint64_t)d * n + imid[d]];
     }
   }
   int sd = 0;
@@ -79,16 +100,15 @@ __device__ __forceinline__ SegStats seg_stats(Pos3c pos, Lists L, int level, uin
       sd = d;
     }
   }
-  const uint32_t half = len / 2, mid = a + half;
-  const uint32_t mid_id = L.l[sd][mid];
   SegStats r;
   r.a = a;
   r.len = len;
   r.sd = (uint32_t)sd;
   r.mid = mid;
-  r.rmid = rk[(uint64_t)sd * n + mid_id];
+  r.rmid = sd == 0 ? rmd[0] : (sd == 1 ? rmd[1] : rmd[2]);
+  r.par = par;
   if (writer) {
-    const double split_val = pos.p[sd][mid_id];
+    const double split_val = sd == 0 ? vmid[0] : (sd == 1 ? vmid[1] : vmid[2]);
     const uint32_t nleft = (uint32_t)subtree_nodes(half, mp, layout);
     WNode* nd = &nodes[node];
     nd->size2 = __dmul_rn(ext, ext);
@@ -96,148 +116,27 @@ __device__ __forceinline__ SegStats seg_stats(Pos3c pos, Lists L, int level, uin
     nd->split_val = split_val;
     nd->a = node + 1 + nleft;
     nd->b = WN_INTERNAL | (uint32_t)sd;
-    tsd[off + s] = (uint8_t)sd;
-    tmid[off + s] = mid;
-    tmr[off + s] = r.rmid;
+    const uint32_t cpar = par ^ (7u & ~(1u << sd));  // every list but the split dimension's changes buffer
     const uint32_t coff = 2 * nseg - 1;
-    tstart[coff + 2 * s] = a;
-    tlen[coff + 2 * s] = half;
-    tnode[coff + 2 * s] = node + 1;
-    tstart[coff + 2 * s + 1] = mid;
-    tlen[coff + 2 * s + 1] = len - half;
-    tnode[coff + 2 * s + 1] = node + 1 + nleft;
+    tseg[coff + 2 * s] = make_uint4(a, half, node + 1, cpar);
+    tseg[coff + 2 * s + 1] = make_uint4(mid, len - half, node + 1 + nleft, cpar);
   }
   return r;
 }
 
-// "goes left" is decided without any per-level flag pass: rk[d][id] is the rank of particle id in the INITIAL sorted
-// list of dimension d (sort.cu).  Stable partitions keep every segment of list d ordered by rk[d], so the left half of
-// a node split along sd is exactly { id : rk[sd][id] < rk[sd][id of the element at mid] } (tmr[] holds that rank).
-__global__ void __launch_bounds__(LVL_THREADS)
-level_count(Pos3c pos, Lists L, int level, uint32_t cps, uint32_t mp, int layout, uint32_t* __restrict__ tstart,
-            uint32_t* __restrict__ tlen, uint32_t* __restrict__ tnode, uint32_t* __restrict__ tmid,
-            uint8_t* __restrict__ tsd, WNode* __restrict__ nodes, const uint32_t* __restrict__ rk, uint32_t n,
-            uint32_t* __restrict__ tmr, uint32_t* __restrict__ cnt, const uint32_t* __restrict__ flat) {
-  pdl_sync();
-  __shared__ uint32_t wsum[LVL_THREADS / 32];
-  __shared__ SegStats st;
-  const uint32_t seg = blockIdx.x / cps, chunk = blockIdx.x % cps, e = blockIdx.y;
-  const uint32_t nseg = 1u << level;
-  if (flat[e]) return;  // (dimension 0 is never flat: its chunk-0 CTA is the writer)
-  if (threadIdx.x == 0)
-    st = seg_stats(pos, L, level, seg, mp, layout, tstart, tlen, tnode, tmid, tsd, nodes, flat, rk, n, tmr,
-                   chunk == 0 && e == 0);
-  __syncthreads();
-  if (st.sd == e) return;  // the split-dimension list is already partitioned
-  const uint32_t a = st.a, len = st.len, rmid = st.rmid;
-  const uint32_t* lst = L.l[e];
-  const uint32_t* rks = rk + (uint64_t)st.sd * n;
-  uint32_t c = 0;
-#pragma unroll
-  for (int k = 0; k < LVL_CHUNK / LVL_THREADS; ++k) {
-    uint32_t o = chunk * LVL_CHUNK + k * LVL_THREADS + threadIdx.x;
-    if (o < len) c += (rks[lst[a + o]] < rmid);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t t = 0;
-#pragma unroll
-    for (int k = 0; k < LVL_THREADS / 32; ++k) t += wsum[k];
-    cnt[((uint64_t)e * nseg + seg) * cps + chunk] = t;
-  }
-}
-
-// stable partition of list e inside each segment (copy for the split-dimension list)
-__global__ void __launch_bounds__(LVL_THREADS, 8) level_scatter(Lists Lin, Lists Lout, int level, uint32_t cps,
-                                                             const uint32_t* __restrict__ tstart,
-                                                             const uint32_t* __restrict__ tlen,
-                                                             const uint32_t* __restrict__ tmid,
-                                                             const uint8_t* __restrict__ tsd,
-                                                             const uint32_t* __restrict__ rk, uint32_t n,
-                                                             const uint32_t* __restrict__ tmr,
-                                                             const uint32_t* __restrict__ cnt,
-                                                             const uint32_t* __restrict__ flat) {
-  pdl_sync();
-  constexpr int IPT = LVL_CHUNK / LVL_THREADS;  // 8
-  __shared__ uint32_t wtot[LVL_THREADS / 32];
-  const uint32_t seg = blockIdx.x / cps, chunk = blockIdx.x % cps, e = blockIdx.y;
-  if (flat[e]) return;
-  const uint32_t nseg = 1u << level, off = nseg - 1;
-  const uint32_t a = tstart[off + seg], len = tlen[off + seg], mid = tmid[off + seg];
-  const uint32_t* lin = Lin.l[e];
-  uint32_t* lout = Lout.l[e];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint32_t lt = (1u << lane) - 1u;
-  const uint32_t wbase_off = chunk * LVL_CHUNK + w * (32 * IPT);
-
-  if (tsd[off + seg] == e) {
-#pragma unroll
-    for (int k = 0; k < IPT; ++k) {
-      uint32_t o = wbase_off + k * 32 + lane;
-      if (o < len) lout[a + o] = lin[a + o];
-    }
-    return;
-  }
-  const uint32_t* rks = rk + (uint64_t)tsd[off + seg] * n;
-  const uint32_t rmid = tmr[off + seg];
-  uint32_t id[IPT], bl[IPT];
-  uint32_t wl = 0;
-#pragma unroll
-  for (int k = 0; k < IPT; ++k) {
-    uint32_t o = wbase_off + k * 32 + lane;
-    bool valid = o < len;
-    id[k] = valid ? lin[a + o] : 0u;
-    bool isleft = valid && (rks[id[k]] < rmid);
-    bl[k] = __ballot_sync(0xffffffffu, isleft);
-    wl += __popc(bl[k]);
-  }
-  if (lane == 0) wtot[w] = wl;
-  __syncthreads();
-  uint32_t wbase = 0;
-#pragma unroll
-  for (int k = 0; k < LVL_THREADS / 32; ++k)
-    if (k < w) wbase += wtot[k];
-  // lefts in the earlier chunks of this segment: block-wide sum of their counts (replaces a separate scan kernel)
-  __shared__ uint32_t lbsum[LVL_THREADS / 32];
-  uint32_t lb = 0;
-  {
-    const uint32_t* row = cnt + ((uint64_t)e * nseg + seg) * cps;
-    for (uint32_t k = threadIdx.x; k < chunk; k += LVL_THREADS) lb += row[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lb += __shfl_xor_sync(0xffffffffu, lb, o);
-    if (lane == 0) lbsum[w] = lb;
-    __syncthreads();
-    lb = 0;
-#pragma unroll
-    for (int k = 0; k < LVL_THREADS / 32; ++k) lb += lbsum[k];
-  }
-  const uint32_t leftbase = lb;
-  uint32_t pre = wbase;
-#pragma unroll
-  for (int k = 0; k < IPT; ++k) {
-    uint32_t o = wbase_off + k * 32 + lane;
-    if (o < len) {
-      uint32_t lrank = leftbase + pre + __popc(bl[k] & lt);  // lefts before me in the segment
-      bool isleft = (bl[k] >> lane) & 1u;
-      uint32_t dst = isleft ? a + lrank : mid + (o - lrank);
-      lout[dst] = id[k];
-    }
-    pre += __popc(bl[k]);
-  }
-}
-
-// ---- one kernel per global level: stable partition of every list inside every segment, single pass.
-// A CTA owns one chunk (LVL_CHUNK entries) of one segment of one list.  It takes a ticket (CTAs are numbered in the
-// order they START, so a CTA only ever waits for CTAs that are already running), evaluates the segment statistics,
-// flags its entries (left = initial rank along the split dimension below the median's), and obtains the number of
-// lefts in the earlier chunks of its segment by decoupled look-back over per-chunk status words
+// ---- one kernel per global level: stable partition of every list (but the split dimension's) inside every segment,
+// single pass.  "Goes left" is decided without any per-level flag pass: rk[d][id] is the rank of particle id in the
+// INITIAL sorted list of dimension d (sort.cu).  Stable partitions keep every segment of list d ordered by rk[d], so the
+// left half of a node split along sd is exactly { id : rk[sd][id] < rk[sd][id of the element at mid] }.
+// A CTA owns one chunk (LVL_CHUNK slots) of one segment, for every list that has to move (one list for planar inputs,
+// two otherwise).  It takes a ticket (CTAs are numbered in the order they START, so a CTA only ever waits for CTAs
+// that are already running), evaluates the segment statistics, flags its entries and obtains the number of lefts in
+// the earlier chunks of its segment by decoupled look-back over per-chunk status words
 //     epoch (30 bits) | state (2 bits: 1 = chunk count, 2 = inclusive prefix) | value (32 bits)
 // written and polled as single 64-bit words.  The epoch (build counter * 64 + level + 1) makes stale words of earlier
-// launches unreadable, so the array is never cleared.  This replaces the count + scatter kernel pair (which read the
-// lists and gathered the ranks twice and paid two launch latencies per level).
+// launches unreadable, so the array is never cleared.  (History: a count + scatter kernel pair per level; then one
+// look-back kernel with a CTA per (list, chunk) that copied the split-dimension list — two thirds of those CTAs only
+// learnt that they had nothing to partition.)
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
@@ -247,11 +146,10 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(LVL_THREADS)
-level_partition(Pos3c pos, Lists Lin, Lists Lout, int level, uint32_t cps, uint32_t mp, int layout,
-                uint32_t* __restrict__ tstart, uint32_t* __restrict__ tlen, uint32_t* __restrict__ tnode,
-                uint32_t* __restrict__ tmid, uint8_t* __restrict__ tsd, WNode* __restrict__ nodes,
-                const uint32_t* __restrict__ rk, uint32_t n, uint32_t* __restrict__ tmr,
+template <int MINB>
+__global__ void __launch_bounds__(LVL_THREADS, MINB)
+level_partition(Pos3c pos, Lists L, int level, uint32_t cps, uint32_t mp, int layout, uint4* __restrict__ tseg,
+                WNode* __restrict__ nodes, const uint32_t* __restrict__ rk, uint32_t n,
                 unsigned long long* __restrict__ status, uint32_t* __restrict__ lvl_ctl,
                 const uint32_t* __restrict__ flat) {
   pdl_sync();
@@ -261,102 +159,92 @@ level_partition(Pos3c pos, Lists Lin, Lists Lout, int level, uint32_t cps, uint3
   __shared__ uint32_t s_ticket, s_leftbase;
   if (threadIdx.x == 0) s_ticket = atomicAdd(&lvl_ctl[level], 1u);
   __syncthreads();
-  const uint32_t nseg = 1u << level, off = nseg - 1, gx = nseg * cps;
-  const uint32_t e = s_ticket / gx, bx = s_ticket % gx;
-  const uint32_t seg = bx / cps, chunk = bx % cps;
-  if (flat[e]) return;  // (dimension 0 is never flat: its chunk-0 CTA is the writer)
+  const uint32_t nseg = 1u << level;
+  const uint32_t seg = s_ticket / cps, chunk = s_ticket % cps;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
-  if (threadIdx.x == 0)
-    st = seg_stats(pos, Lin, level, seg, mp, layout, tstart, tlen, tnode, tmid, tsd, nodes, flat, rk, n, tmr,
-                   chunk == 0 && e == 0);
-  // the entries of this chunk are loaded while thread 0 walks the dependent loads of the statistics
-  const uint32_t a = tstart[off + seg], len = tlen[off + seg];
-  const uint32_t* lin = Lin.l[e];
-  uint32_t* lout = Lout.l[e];
-  const uint32_t wbase_off = chunk * LVL_CHUNK + w * (32 * IPT);
-  uint32_t id[IPT];
-#pragma unroll
-  for (int k = 0; k < IPT; ++k) {
-    const uint32_t o = wbase_off + k * 32 + lane;
-    id[k] = o < len ? lin[a + o] : 0u;
-  }
+  if (threadIdx.x == 0) st = seg_stats(pos, L, level, seg, mp, layout, tseg, nodes, flat, rk, n, chunk == 0);
   __syncthreads();
-  if (st.sd == e) {  // the split-dimension list is already partitioned: copy
+  const uint32_t a = st.a, len = st.len, sd = st.sd, rmid = st.rmid, mid = st.mid, par = st.par;
+  if (chunk * (uint32_t)LVL_CHUNK >= len) return;  // (segments of a level differ by at most one slot; nobody looks back at these)
+  const uint32_t* rks = rk + (uint64_t)sd * n;
+  const uint32_t wbase_off = chunk * LVL_CHUNK + w * (32 * IPT);
+  const unsigned long long epoch = ((unsigned long long)((lvl_ctl[LC_EPOCH] << 6) + (uint32_t)level + 1u) & 0x3fffffffull) << 34;
+  for (uint32_t e = 0; e < 3; ++e) {
+    if (e == sd || flat[e]) continue;  // the split-dimension list is already partitioned and stays in its buffer
+    const uint32_t buf = (par >> e) & 1u;
+    const uint32_t* lin = L.l[buf][e];
+    uint32_t* lout = L.l[buf ^ 1u][e];
+    uint32_t id[IPT], bl[IPT];
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
       const uint32_t o = wbase_off + k * 32 + lane;
-      if (o < len) lout[a + o] = id[k];
+      id[k] = o < len ? lin[a + o] : 0u;
     }
-    return;
-  }
-  const uint32_t* rks = rk + (uint64_t)st.sd * n;
-  const uint32_t rmid = st.rmid, mid = st.mid;
-  uint32_t bl[IPT];
-  uint32_t wl = 0;
+    uint32_t wl = 0;
 #pragma unroll
-  for (int k = 0; k < IPT; ++k) {
-    const uint32_t o = wbase_off + k * 32 + lane;
-    const bool isleft = o < len && (rks[id[k]] < rmid);
-    bl[k] = __ballot_sync(0xffffffffu, isleft);
-    wl += __popc(bl[k]);
-  }
-  if (lane == 0) wtot[w] = wl;
-  __syncthreads();
-  uint32_t wbase = 0, total = 0;
+    for (int k = 0; k < IPT; ++k) {
+      const uint32_t o = wbase_off + k * 32 + lane;
+      const bool isleft = o < len && (rks[id[k]] < rmid);
+      bl[k] = __ballot_sync(0xffffffffu, isleft);
+      wl += __popc(bl[k]);
+    }
+    if (lane == 0) wtot[w] = wl;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
 #pragma unroll
-  for (int k = 0; k < LVL_THREADS / 32; ++k) {
-    if (k < w) wbase += wtot[k];
-    total += wtot[k];
-  }
-  if (w == 0) {  // publish this chunk's count, look back for the lefts of the earlier chunks, publish the prefix
-    const unsigned long long epoch = ((unsigned long long)((lvl_ctl[LC_EPOCH] << 6) + (uint32_t)level + 1u) & 0x3fffffffull) << 34;
-    unsigned long long* row = status + ((uint64_t)e * nseg + seg) * cps;
-    uint32_t excl = 0;
-    if (chunk > 0) {
-      if (lane == 0) st_status(&row[chunk], epoch | (1ull << 32) | total);
-      int j = (int)chunk - 1;
-      uint32_t polls = 0;
-      for (;;) {
-        const int idx = j - lane;
-        unsigned long long v = epoch | (2ull << 32);  // before chunk 0: an inclusive prefix of 0
-        if (idx >= 0) v = ld_status(&row[idx]);
-        const uint32_t state = ((v >> 34) == (epoch >> 34)) ? (uint32_t)(v >> 32) & 3u : 0u;
-        const uint32_t have = __ballot_sync(0xffffffffu, state != 0u);
-        const uint32_t incl = __ballot_sync(0xffffffffu, state == 2u);
-        const int first = incl ? __ffs(incl) - 1 : 32;                      // nearest inclusive prefix in this window
-        const uint32_t need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);  // lanes 0..first
-        if ((have & need) == need) {
-          uint32_t val = (lane <= first) ? (uint32_t)v : 0u;
+    for (int k = 0; k < LVL_THREADS / 32; ++k) {
+      if (k < w) wbase += wtot[k];
+      total += wtot[k];
+    }
+    if (w == 0) {  // publish this chunk's count, look back for the lefts of the earlier chunks, publish the prefix
+      unsigned long long* row = status + ((uint64_t)e * nseg + seg) * cps;
+      uint32_t excl = 0;
+      if (chunk > 0) {
+        if (lane == 0) st_status(&row[chunk], epoch | (1ull << 32) | total);
+        int j = (int)chunk - 1;
+        uint32_t polls = 0;
+        for (;;) {
+          const int idx = j - lane;
+          unsigned long long v = epoch | (2ull << 32);  // before chunk 0: an inclusive prefix of 0
+          if (idx >= 0) v = ld_status(&row[idx]);
+          const uint32_t state = ((v >> 34) == (epoch >> 34)) ? (uint32_t)(v >> 32) & 3u : 0u;
+          const uint32_t have = __ballot_sync(0xffffffffu, state != 0u);
+          const uint32_t incl = __ballot_sync(0xffffffffu, state == 2u);
+          const int first = incl ? __ffs(incl) - 1 : 32;                      // nearest inclusive prefix in this window
+          const uint32_t need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);  // lanes 0..first
+          if ((have & need) == need) {
+            uint32_t val = (lane <= first) ? (uint32_t)v : 0u;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-          excl += val;
-          if (first < 32) break;
-          j -= 32;
-        } else if (++polls > (1u << 22)) {  // a predecessor never published (cannot happen): do not hang the GPU
-          if (lane == 0) lvl_ctl[LC_ERR] = 1u;
-          break;
+            for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+            excl += val;
+            if (first < 32) break;
+            j -= 32;
+          } else if (++polls > (1u << 22)) {  // a predecessor never published (cannot happen): do not hang the GPU
+            if (lane == 0) lvl_ctl[LC_ERR] = 1u;
+            break;
+          }
         }
       }
+      if (lane == 0) {
+        st_status(&row[chunk], epoch | (2ull << 32) | (unsigned long long)(excl + total));
+        s_leftbase = excl;
+      }
     }
-    if (lane == 0) {
-      st_status(&row[chunk], epoch | (2ull << 32) | (unsigned long long)(excl + total));
-      s_leftbase = excl;
-    }
-  }
-  __syncthreads();
-  const uint32_t leftbase = s_leftbase;
-  uint32_t pre = wbase;
+    __syncthreads();
+    const uint32_t leftbase = s_leftbase;
+    uint32_t pre = wbase;
 #pragma unroll
-  for (int k = 0; k < IPT; ++k) {
-    const uint32_t o = wbase_off + k * 32 + lane;
-    if (o < len) {
-      const uint32_t lrank = leftbase + pre + __popc(bl[k] & lt);  // lefts before me in the segment
-      const bool isleft = (bl[k] >> lane) & 1u;
-      const uint32_t dst = isleft ? a + lrank : mid + (o - lrank);
-      lout[dst] = id[k];
+    for (int k = 0; k < IPT; ++k) {
+      const uint32_t o = wbase_off + k * 32 + lane;
+      if (o < len) {
+        const uint32_t lrank = leftbase + pre + __popc(bl[k] & lt);  // lefts before me in the segment
+        const bool isleft = (bl[k] >> lane) & 1u;
+        const uint32_t dst = isleft ? a + lrank : mid + (o - lrank);
+        lout[dst] = id[k];
+      }
+      pre += __popc(bl[k]);
     }
-    pre += __popc(bl[k]);
   }
 }
 
@@ -396,8 +284,7 @@ static inline size_t bot_smem_bytes(uint32_t mp) { return sizeof(BotSmem) + (bot
 
 __global__ void __launch_bounds__(BOT_THREADS, 4)
 build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_t mp, int layout,
-             const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ tlen,
-             const uint32_t* __restrict__ tnode, uint32_t* __restrict__ inv, WNode* __restrict__ nodes,
+             const uint4* __restrict__ tseg, uint32_t* __restrict__ inv, WNode* __restrict__ nodes,
              double4* __restrict__ ms, uint32_t* __restrict__ perm, uint32_t* __restrict__ rank,
              PosM* __restrict__ posm, const uint32_t* __restrict__ flat, uint32_t heap) {
   pdl_sync();
@@ -406,11 +293,15 @@ build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t lt = (1u << lane) - 1u;
   const uint32_t off = (1u << level) - 1;
-  const uint32_t a0 = tstart[off + blockIdx.x], len0 = tlen[off + blockIdx.x], node0 = tnode[off + blockIdx.x];
+  const uint4 tb = tseg[off + blockIdx.x];
+  const uint32_t a0 = tb.x, len0 = tb.y, node0 = tb.z;
+  const uint32_t* const lx = L.l[tb.w & 1u][0];  // the buffer each list of this segment ended up in
+  const uint32_t* const ly = L.l[(tb.w >> 1) & 1u][1];
+  const uint32_t* const lz = L.l[(tb.w >> 2) & 1u][2];
 
   // ---- load: local slot j <-> id of the j-th entry of the x list
   for (uint32_t j = tid; j < len0; j += BOT_THREADS) {
-    uint32_t g = L.l[0][a0 + j];
+    uint32_t g = lx[a0 + j];
     S.gid[j] = g;
     inv[g] = j;
     S.lst[0][0][j] = (uint16_t)j;
@@ -429,8 +320,8 @@ build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_
   __syncthreads();
   const bool flat1 = flat[1] != 0, flat2 = flat[2] != 0;
   for (uint32_t j = tid; j < len0; j += BOT_THREADS) {
-    if (!flat1) S.lst[0][1][j] = (uint16_t)inv[L.l[1][a0 + j]];
-    if (!flat2) S.lst[0][2][j] = (uint16_t)inv[L.l[2][a0 + j]];
+    if (!flat1) S.lst[0][1][j] = (uint16_t)inv[ly[a0 + j]];
+    if (!flat2) S.lst[0][2][j] = (uint16_t)inv[lz[a0 + j]];
   }
   __syncthreads();
 
@@ -451,13 +342,15 @@ build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_
         if (2 * h + 1 < heap) S.tab[2 * h].kind = S.tab[2 * h + 1].kind = 2;
         continue;
       }
-      double mn[3], mx[3];
+      const uint32_t half = t.len / 2, mid = t.a + half;
+      double mn[3], mx[3], vmid[3];  // the median coordinate of every dimension travels with the ends: one round trip
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        mn[d] = mx[d] = 0.0;
+        mn[d] = mx[d] = vmid[d] = 0.0;
         if (d == 0 || !(d == 1 ? flat1 : flat2)) {
           mn[d] = pos.p[d][S.gid[S.lst[cur][d][t.a]]];
           mx[d] = pos.p[d][S.gid[S.lst[cur][d][t.a + t.len - 1]]];
+          vmid[d] = pos.p[d][S.gid[S.lst[cur][d][mid]]];
         }
       }
       int sd = 0;
@@ -470,8 +363,7 @@ build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_
           sd = d;
         }
       }
-      const uint32_t half = t.len / 2, mid = t.a + half;
-      const double split_val = pos.p[sd][S.gid[S.lst[cur][sd][mid]]];
+      const double split_val = sd == 0 ? vmid[0] : (sd == 1 ? vmid[1] : vmid[2]);
       const uint32_t nleft = (uint32_t)subtree_nodes(half, mp, layout);
       WNode* nd = &nodes[t.node];
       nd->size2 = __dmul_rn(ext, ext);
@@ -639,13 +531,13 @@ build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_
 }
 
 // m / cm for the global levels (single CTA; at most a few thousand nodes)
-__global__ void __launch_bounds__(1024) build_topup(int l0, const uint32_t* __restrict__ tnode,
+__global__ void __launch_bounds__(1024) build_topup(int l0, const uint4* __restrict__ tseg,
                                                     WNode* __restrict__ nodes, double4* __restrict__ ms) {
   pdl_sync();
   for (int lev = l0 - 1; lev >= 0; --lev) {
     const uint32_t nn = 1u << lev, off = nn - 1;
     for (uint32_t s = threadIdx.x; s < nn; s += blockDim.x) {
-      const uint32_t node = tnode[off + s];
+      const uint32_t node = tseg[off + s].z;
       WNode* nd = &nodes[node];
       const double4 l = ms[node + 1], r = ms[nd->a];
       double4 t = make_double4(__dadd_rn(l.x, r.x), __dadd_rn(l.y, r.y), __dadd_rn(l.z, r.z), __dadd_rn(l.w, r.w));
@@ -689,32 +581,31 @@ int build_tree(Ctx* c) {
     g_bottom_attr_set = true;
   }
   Pos3c pos = {{c->pos[0], c->pos[1], c->pos[2]}};
-  KDNB_LAUNCH(c, build_root, 1, 64, 0, c->tstart, c->tlen, c->tnode, n, c->lvl_ctl);
-  static const bool split_kernels = getenv("KDNB_LEVEL_SPLIT") != nullptr;  // profiling knob: count + scatter kernel pair
-  int cur = 0;
+  Lists L = {{{c->list[0], c->list[0] + n, c->list[0] + 2ull * n}, {c->list[1], c->list[1] + n, c->list[1] + 2ull * n}}};
+  KDNB_LAUNCH(c, build_root, 1, 64, 0, c->tseg, n, c->lvl_ctl);
+  // Resident CTAs per SM the partition kernel's register budget is sized for: 4 (63 registers, no spills) while a
+  // level fits the GPU in about a wave, 8 (32 registers, 76 bytes spilled) when a level is many waves deep and the extra
+  // CTAs hide the look-back and gather latencies (N = 10M: build 4.88 -> 4.62 ms; N = 1M: no difference).
+  // KDNB_LVL_MINB overrides (profiling knob).
+  static const int lvl_minb_env = [] {
+    const char* e = getenv("KDNB_LVL_MINB");
+    return e ? atoi(e) : 0;
+  }();
+  const int lvl_minb = lvl_minb_env ? lvl_minb_env : ((c->n + LVL_CHUNK - 1) / LVL_CHUNK > 8ull * c->num_sms ? 8 : 4);
   for (int lev = 0; lev < c->l0; ++lev) {
     const uint32_t nseg = 1u << lev;
     const uint32_t maxlen = (uint32_t)((c->n + nseg - 1) >> lev);
     const uint32_t cps = (maxlen + LVL_CHUNK - 1) / LVL_CHUNK;
-    Lists Lin = {{c->list[cur], c->list[cur] + n, c->list[cur] + 2ull * n}};
-    Lists Lout = {{c->list[cur ^ 1], c->list[cur ^ 1] + n, c->list[cur ^ 1] + 2ull * n}};
-    if (split_kernels) {
-      KDNB_LAUNCH(c, level_count, dim3(nseg * cps, 3), LVL_THREADS, 0, pos, Lin, lev, cps, c->mp, c->layout, c->tstart,
-                  c->tlen, c->tnode, c->tmid, c->tsd, c->nodes, c->rk, n, c->tmr, c->chunk_cnt, c->flat);
-      KDNB_LAUNCH(c, level_scatter, dim3(nseg * cps, 3), LVL_THREADS, 0, Lin, Lout, lev, cps, c->tstart, c->tlen,
-                  c->tmid, c->tsd, c->rk, n, c->tmr, c->chunk_cnt, c->flat);
-    } else {
-      KDNB_LAUNCH(c, level_partition, nseg * cps * 3, LVL_THREADS, 0, pos, Lin, Lout, lev, cps, c->mp, c->layout,
-                  c->tstart, c->tlen, c->tnode, c->tmid, c->tsd, c->nodes, c->rk, n, c->tmr,
-                  reinterpret_cast<unsigned long long*>(c->lvl_status), c->lvl_ctl, c->flat);
-    }
-    cur ^= 1;
+#define KDNB_LVL_ARGS pos, L, lev, cps, c->mp, c->layout, c->tseg, c->nodes, c->rk, n, \
+                      reinterpret_cast<unsigned long long*>(c->lvl_status), c->lvl_ctl, c->flat
+    if (lvl_minb == 8) KDNB_LAUNCH(c, (level_partition<8>), nseg * cps, LVL_THREADS, 0, KDNB_LVL_ARGS);
+    else if (lvl_minb == 6) KDNB_LAUNCH(c, (level_partition<6>), nseg * cps, LVL_THREADS, 0, KDNB_LVL_ARGS);
+    else KDNB_LAUNCH(c, (level_partition<4>), nseg * cps, LVL_THREADS, 0, KDNB_LVL_ARGS);
+#undef KDNB_LVL_ARGS
   }
-  Lists Lb = {{c->list[cur], c->list[cur] + n, c->list[cur] + 2ull * n}};
-  KDNB_LAUNCH(c, build_bottom, 1u << c->l0, BOT_THREADS, bot_smem_bytes(c->mp), pos, c->pm, Lb, c->l0, c->mp,
-              c->layout, c->tstart, c->tlen, c->tnode, c->inv, c->nodes, c->ms, c->perm, c->rank, c->posm, c->flat,
-              bot_heap(c->mp));
-  if (c->l0 > 0) KDNB_LAUNCH(c, build_topup, 1, 1024, 0, c->l0, c->tnode, c->nodes, c->ms);
+  KDNB_LAUNCH(c, build_bottom, 1u << c->l0, BOT_THREADS, bot_smem_bytes(c->mp), pos, c->pm, L, c->l0, c->mp, c->layout,
+              c->tseg, c->inv, c->nodes, c->ms, c->perm, c->rank, c->posm, c->flat, bot_heap(c->mp));
+  if (c->l0 > 0) KDNB_LAUNCH(c, build_topup, 1, 1024, 0, c->l0, c->tseg, c->nodes, c->ms);
   KDNB_CHECK_LAUNCH(c);
   c->tree_valid = true;
   c->map_valid = true;

@@ -63,14 +63,8 @@ struct Ctx {
   uint32_t* flat = nullptr;                // [3] 1 = all coordinates of that dimension equal (lives behind digit_tot); [3] planar walk
   uint64_t* sort_state = nullptr;          // [16] key range, 32-bit key scaling, need64 flag (sort.cu)
   uint32_t* rk = nullptr;                  // [3][n] rank of every particle in the initial sorted list of each dimension
-  uint32_t* tmr = nullptr;                 // level table: rk of the median element of every segment
-  uint32_t* tstart = nullptr;              // level tables, level l at offset 2^l - 1
-  uint32_t* tlen = nullptr;
-  uint32_t* tnode = nullptr;
-  uint32_t* tmid = nullptr;
-  uint8_t* tsd = nullptr;
+  uint4* tseg = nullptr;                   // level table, level l at offset 2^l - 1: {first slot, length, node, buffer bits}
   uint32_t* inv = nullptr;                 // [n] id -> local slot inside a bottom segment
-  uint32_t* chunk_cnt = nullptr;           // [3][nseg][chunks] left counts per chunk
   uint64_t* lvl_status = nullptr;          // [3][nseg][chunks] look-back status words of level_partition (build.cu)
   uint32_t* lvl_ctl = nullptr;             // [72] per-level tickets, build epoch, timeout flag
   uint64_t table_cap = 0, chunk_cap = 0;

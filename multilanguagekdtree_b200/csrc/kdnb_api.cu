@@ -105,15 +105,9 @@ static void free_all(Ctx* c) {
   fr(c->digit_tot);
   fr(c->sort_state);
   fr(c->rk);
-  fr(c->tmr);
   fr(c->pm);
   fr(c->inv);
-  fr(c->tstart);
-  fr(c->tlen);
-  fr(c->tnode);
-  fr(c->tmid);
-  fr(c->tsd);
-  fr(c->chunk_cnt);
+  fr(c->tseg);
   fr(c->lvl_status);
   fr(c->lvl_ctl);
   fr(c->nodes);
@@ -266,15 +260,9 @@ static int plan(Ctx* c, uint64_t n) {
     if (!rc) c->flat = c->digit_tot + 3 * 256;
     if (!rc) rc = dev_alloc(c, &c->sort_state, 16);
     if (!rc) rc = dev_alloc(c, &c->rk, 3 * n);
-    if (!rc) rc = dev_alloc(c, &c->tmr, table);
     if (!rc) rc = dev_alloc(c, &c->pm, n);
     if (!rc) rc = dev_alloc(c, &c->inv, n);
-    if (!rc) rc = dev_alloc(c, &c->tstart, table);
-    if (!rc) rc = dev_alloc(c, &c->tlen, table);
-    if (!rc) rc = dev_alloc(c, &c->tnode, table);
-    if (!rc) rc = dev_alloc(c, &c->tmid, table);
-    if (!rc) rc = dev_alloc(c, &c->tsd, table);
-    if (!rc) rc = dev_alloc(c, &c->chunk_cnt, chunks);
+    if (!rc) rc = dev_alloc(c, &c->tseg, table);
     if (!rc) rc = dev_alloc(c, &c->lvl_status, chunks);
     if (!rc) rc = dev_alloc(c, &c->lvl_ctl, 72);
     if (!rc) KDNB_CUDA_TRY(c, cudaMemsetAsync(c->lvl_status, 0, chunks * sizeof(uint64_t), c->stream));
