@@ -55,6 +55,18 @@ struct Status {
     }                                                                                               \
   } while (0)
 
+// ---- MUFU.RSQ64H: the hardware's reciprocal-square-root estimate of an f64 (relative error < 2^-22, low word 0).
+// (KDNB_SIMT: the CPU execution model of tests/devtools/simt, a development aid — never defined in the product build.)
+__device__ __forceinline__ double rsqrt_estimate(double x) {
+#ifdef KDNB_SIMT
+  return simt::rsqrt_approx(x);
+#else
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+#endif
+}
+
 // ---- order-preserving key of an f64 coordinate (canonical order: -0.0 == +0.0, ties by index)
 __host__ __device__ inline uint64_t f64_key(double x) {
   x = x + 0.0;  // -0.0 -> +0.0 (round-to-nearest)

@@ -115,8 +115,7 @@ __device__ __forceinline__ void drain2(W2Smem<EXACT>& S, int cnt, int lane, doub
       }
 #pragma unroll
       for (int j = 0; j < DW; ++j) {
-double r;
-        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d2[j]));
+        const double r = rsqrt_estimate(d2[j]);
         y[j] = __hiloint2double(use[j] ? __double2hiint(r) : 0, 0);
       }
 #pragma unroll

@@ -47,8 +47,7 @@ struct __align__(32) Rec32 {
 // r^-3 = y0^3 * (1 - e)^(-3/2) = y0^3 * (1 + 1.5 e + 1.875 e^2 + O(e^3)); O(e^3) < 2^-63.  No special cases:
 // callers discard the result by select when the pair is masked out (d2 == 0 gives NaN there).
 __device__ __forceinline__ double neg_m_over_r3_fast(double mneg, double d2) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d2));
+  const double y = rsqrt_estimate(d2);
   const double y2 = __dmul_rn(y, y);
   const double e = fma(-d2, y2, 1.0);
   const double y3 = __dmul_rn(y, y2);
@@ -144,7 +143,7 @@ __device__ __forceinline__ void drain_list(const Rec32* __restrict__ lpos, const
 #pragma unroll
       for (int j = 0; j < DW; ++j) d2[j] = fma(dz[j], dz[j], d2[j]);
 #pragma unroll
-      for (int j = 0; j < DW; ++j) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[j]) : "d"(d2[j]));
+      for (int j = 0; j < DW; ++j) y[j] = rsqrt_estimate(d2[j]);
 #pragma unroll
       for (int j = 0; j < DW; ++j) y2[j] = __dmul_rn(y[j], y[j]);
 #pragma unroll

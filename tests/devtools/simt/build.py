@@ -1,0 +1,41 @@
+"""Development aid: compile the kernel sources of multilanguagekdtree_b200/csrc with g++ against the SIMT shim in this
+directory (cuda_runtime.h, simt_runtime.cpp) into _build/libkdnb_simt.so — the same C ABI, every CUDA thread a fiber on
+the CPU.  Not product, not a fallback: nothing under multilanguagekdtree_b200/ knows about it (see run.py)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", "..", ".."))
+CSRC = os.path.join(ROOT, "multilanguagekdtree_b200", "csrc")
+OUT = os.path.join(HERE, "_build", "libkdnb_simt.so")
+CU = ["kdnb_api.cu", "sort.cu", "build.cu", "walk.cu", "kick.cu", "select.cu", "peak.cu"]
+
+
+def build(verbose: bool = False) -> str:
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    objs = []
+    flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-fopenmp", "-ffp-contract=off", "-mfma", "-Wno-unknown-pragmas",
+             "-Wno-attributes", "-I", HERE, "-I", CSRC]
+    for f in CU + ["simt_runtime.cpp"]:
+        src = os.path.join(CSRC, f) if f.endswith(".cu") else os.path.join(HERE, f)
+        obj = os.path.join(HERE, "_build", f.replace(".cu", ".o").replace(".cpp", ".o"))
+        deps = [src, os.path.join(HERE, "cuda_runtime.h")] + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".hpp"))]
+        if os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps):
+            objs.append(obj)
+            continue
+        cmd = ["g++", *flags, "-x", "c++", "-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ failed on {f}:\n" + r.stderr[-6000:])
+        if verbose and r.stderr:
+            print(r.stderr[-2000:])
+        objs.append(obj)
+    r = subprocess.run(["g++", "-shared", "-fopenmp", "-o", OUT, *objs, "-ldl"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stderr[-4000:])
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(verbose="-v" in sys.argv))
