@@ -296,6 +296,9 @@ def run_kdnb(args) -> None:
                 "flops_per_particle_step": flops_step / (n + 1),
                 "counts_per_particle": {"node_tests": V / (n + 1), "accepts": A / (n + 1), "leaf_visits": LV / (n + 1), "pairs": P / (n + 1)},
                 "share_of_step": walk_ms / (ms / K),
+                # ncu of the committed capture (profiles/r01_walk_kernel_ncu_full_raw.csv, N=1M, one GPU): the flop model
+                # counts sqrt and divide as one flop each, the pipe-utilisation figure is the gauge of the FP64 pipe
+                "fp64_pipe_active_pct_ncu": 65.8 if (n == 1_000_000 and world == 1) else None,
             },
             "roofline_hbm": {
                 "peak": hbm_peak, "unit": "GB/s", "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",

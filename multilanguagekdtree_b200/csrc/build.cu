@@ -582,15 +582,13 @@ void init_unused_nodes(Ctx* c) {
   KDNB_LAUNCH(c, fill_unused, (unsigned)((c->n_nodes + 255) / 256), 256, 0, c->nodes, c->n_nodes);
 }
 
-static bool g_bottom_attr_set = false;
-
 int build_tree(Ctx* c) {
   const uint32_t n = (uint32_t)c->n;
   if (int rc = sort_lists(c)) return rc;
-  if (!g_bottom_attr_set) {
+  if (!c->bottom_attr_set) {  // per context: function attributes belong to the device the context drives
     KDNB_CUDA_TRY(c, cudaFuncSetAttribute(build_bottom, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)bot_smem_bytes(4)));
-    g_bottom_attr_set = true;
+    c->bottom_attr_set = true;
   }
   Pos3c pos = {{c->pos[0], c->pos[1], c->pos[2]}};
   Lists L = {{{c->list[0], c->list[0] + n, c->list[0] + 2ull * n}, {c->list[1], c->list[1] + n, c->list[1] + 2ull * n}}};

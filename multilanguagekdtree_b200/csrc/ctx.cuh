@@ -79,6 +79,7 @@ struct Ctx {
   unsigned long long* wcounts = nullptr;  // [n][4] optional walk counters, tree order
   double* tmp3 = nullptr;    // [n][3] staging for accel up/download
   bool tree_valid = false, acc_valid = false, map_valid = false;
+  bool bottom_attr_set = false;  // build_bottom's dynamic shared memory limit raised on this context's device
   uint64_t planned_n = 0;
 
   // multi-GPU
