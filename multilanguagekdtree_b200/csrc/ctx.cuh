@@ -41,6 +41,7 @@ struct Ctx {
 
   // sizes
   uint64_t n = 0;        // particles (N+1 of the reference)
+  bool empty = false;    // an empty particle set was uploaded: every stage is a no-op, as in the reference
   uint64_t cap = 0;      // allocated particle capacity
   uint64_t n_nodes = 0;  // allocate_node_vec length for (n, layout)
   uint64_t node_cap = 0;

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "ctx.cuh"
@@ -35,13 +36,11 @@ struct NcclApi {
   fn_all_gather all_gather = nullptr;
   fn_comm_destroy comm_destroy = nullptr;
   fn_get_error_string get_error_string = nullptr;
-  bool tried = false;
+  std::once_flag once;
 } g_nccl;
 
 bool load_nccl(std::string* why) {
-  if (g_nccl.handle) return true;
-  if (!g_nccl.tried) {
-    g_nccl.tried = true;
+  std::call_once(g_nccl.once, [] {
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* nm : names) {
       g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
@@ -58,10 +57,11 @@ bool load_nccl(std::string* why) {
         g_nccl.handle = nullptr;
       }
     }
-  }
+  });
   if (!g_nccl.handle && why) *why = "libnccl.so.2 could not be loaded";
   return g_nccl.handle != nullptr;
 }
+constexpr int KDNB_MAX_WORLD = 64;  // ranks of one communicator (kdnb_comm_init)
 constexpr int NCCL_FLOAT64 = 8;  // ncclDouble
 constexpr int NCCL_UINT8 = 1;
 }  // namespace
@@ -155,8 +155,8 @@ static int setup_peers(Ctx* c) {
   KDNB_CUDA_TRY(c, cudaMalloc(&dev, sizeof(Rec) * W));
   KDNB_CUDA_TRY(c, cudaMemcpyAsync(dev + c->rank_id, &mine, sizeof(Rec), cudaMemcpyHostToDevice, c->stream));
   int r = g_nccl.all_gather(dev + c->rank_id, dev, sizeof(Rec), NCCL_UINT8, c->nccl_comm, c->stream);
-  std::vector<Rec> all(W);
-  cudaError_t e = cudaMemcpyAsync(all.data(), dev, sizeof(Rec) * W, cudaMemcpyDeviceToHost, c->stream);
+  Rec all[KDNB_MAX_WORLD];  // W <= KDNB_MAX_WORLD (kdnb_comm_init)
+  cudaError_t e = cudaMemcpyAsync(all, dev, sizeof(Rec) * W, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaFree(dev);
   if (r != 0) return c->fail(KDNB_E_NCCL, "ncclAllGather(ipc handles) failed");
@@ -190,8 +190,8 @@ static int setup_peers(Ctx* c) {
   int okv = ok ? 1 : 0;
   KDNB_CUDA_TRY(c, cudaMemcpyAsync(dev2 + c->rank_id, &okv, sizeof(int), cudaMemcpyHostToDevice, c->stream));
   r = g_nccl.all_gather(dev2 + c->rank_id, dev2, sizeof(int), NCCL_UINT8, c->nccl_comm, c->stream);
-  std::vector<int> oks(W);
-  e = cudaMemcpyAsync(oks.data(), dev2, sizeof(int) * W, cudaMemcpyDeviceToHost, c->stream);
+  int oks[KDNB_MAX_WORLD];
+  e = cudaMemcpyAsync(oks, dev2, sizeof(int) * W, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaFree(dev2);
   if (r != 0 || e != cudaSuccess) return c->fail(KDNB_E_NCCL, "peer set-up vote failed");
@@ -224,9 +224,9 @@ static uint64_t shard_slots_for(uint64_t n, int world) { return (((n + world - 1
 
 // (re)plan and (re)allocate for `n` particles
 static int plan(Ctx* c, uint64_t n) {
-  if (n == 0) return c->fail(KDNB_E_INVALID, "particle count must be > 0");
   if (n > 0x7fffff00ull) return c->fail(KDNB_E_INVALID, "particle count exceeds the 32-bit index range of the device path");
   c->n = n;
+  c->empty = false;
   c->n_nodes = subtree_nodes(n, c->mp, c->layout);
   c->ntiles = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
   int l0 = 0;
@@ -416,8 +416,24 @@ void kdnb_destroy(kdnb_ctx* ctx) {
   Ctx* c = &(ctx)->c;                    \
   KDNB_CUDA_TRY(c, cudaSetDevice(c->device))
 
+#define NEED_PARTICLES(c) \
+  if ((c)->n == 0 && !(c)->empty) return (c)->fail(KDNB_E_INVALID, "no particles uploaded")
+
+// `bodies` is empty: the reference's simple_sim then owns an empty acc / indices and the one-node tree of
+// allocate_node_vec(0) (array_kd_tree.rs:45-60), whose node 0 the build writes as Leaf{0, [0; MAX_PARTS]} (:524-529),
+// and every stage loops over nothing.  No device work.
+static int upload_empty(Ctx* c) {
+  c->n = 0;
+  c->empty = true;
+  c->n_nodes = 1;
+  c->planned_n = 0;
+  c->tree_valid = c->acc_valid = c->map_valid = false;
+  return 0;
+}
+
 int kdnb_upload_particles(kdnb_ctx* ctx, const kdnb_particle* aos, uint64_t count) {
   CTX_OR_FAIL(ctx);
+  if (count == 0) return upload_empty(c);
   if (!aos) return c->fail(KDNB_E_INVALID, "null particle array");
   if (int rc = plan(c, count)) return rc;
   KDNB_CUDA_TRY(c, cudaMemcpyAsync(c->aos, aos, count * sizeof(kdnb_particle), cudaMemcpyHostToDevice, c->stream));
@@ -426,8 +442,9 @@ int kdnb_upload_particles(kdnb_ctx* ctx, const kdnb_particle* aos, uint64_t coun
 
 int kdnb_download_particles(kdnb_ctx* ctx, kdnb_particle* out, uint64_t capacity) {
   CTX_OR_FAIL(ctx);
+  NEED_PARTICLES(c);
+  if (c->empty) return 0;
   if (!out) return c->fail(KDNB_E_INVALID, "null output array");
-  if (c->n == 0) return c->fail(KDNB_E_INVALID, "no particles uploaded");
   if (capacity < c->n) return c->fail(KDNB_E_CAPACITY, "output array smaller than the particle count");
   if (int rc = soa_to_aos(c)) return rc;
   KDNB_CUDA_TRY(c, cudaMemcpyAsync(out, c->aos, c->n * sizeof(kdnb_particle), cudaMemcpyDeviceToHost, c->stream));
@@ -439,33 +456,40 @@ uint64_t kdnb_particle_count(const kdnb_ctx* ctx) { return ctx ? ctx->c.n : 0; }
 
 int kdnb_build_tree(kdnb_ctx* ctx) {
   CTX_OR_FAIL(ctx);
-  if (c->n == 0) return c->fail(KDNB_E_INVALID, "no particles uploaded");
+  NEED_PARTICLES(c);
+  if (c->empty) {
+    c->tree_valid = c->map_valid = true;
+    return 0;
+  }
   return build_tree(c);
 }
 
 int kdnb_calc_accel(kdnb_ctx* ctx) {
   CTX_OR_FAIL(ctx);
   if (!c->tree_valid) return c->fail(KDNB_E_INVALID, "kdnb_calc_accel needs kdnb_build_tree on the current positions first");
+  if (c->empty) {
+    c->acc_valid = true;
+    return 0;
+  }
   if (int rc = walk(c)) return rc;
   return exchange(c);
 }
 
 int kdnb_kick_drift(kdnb_ctx* ctx, double dt) {
   CTX_OR_FAIL(ctx);
-  if (c->n == 0) return c->fail(KDNB_E_INVALID, "no particles uploaded");
+  NEED_PARTICLES(c);
   if (!c->map_valid) return c->fail(KDNB_E_INVALID, "kdnb_kick_drift needs the particle->slot map of a previous kdnb_build_tree");
+  if (c->empty) {
+    c->tree_valid = false;
+    return 0;
+  }
   return kick_drift(c, dt);
-}
-
-static void drop_graph(Ctx* c) {
-  if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
-  c->step_graph = nullptr;
-  c->graph_n = 0;
 }
 
 int kdnb_simple_sim(kdnb_ctx* ctx, double dt, int64_t steps) {
   CTX_OR_FAIL(ctx);
-  if (c->n == 0) return c->fail(KDNB_E_INVALID, "no particles uploaded");
+  NEED_PARTICLES(c);
+  if (c->empty) return 0;
   int64_t s = 0;
   // Launch-bound regime (N <= ~1M: ~35 kernels of 5-35 us per step): replay the step as one CUDA graph.  A graph is
   // captured by a call of >= 3 steps, or by the third consecutive call with the same (n, dt) — a caller stepping one
@@ -487,9 +511,7 @@ int kdnb_simple_sim(kdnb_ctx* ctx, double dt, int64_t steps) {
     if (!have) {
       if (int rc = one_step(c, dt)) return rc;
       s = 1;
-    }
-    if (!have) {
-      drop_graph(c);
+      drop_graph_if_any(c);
       const uint64_t l0 = c->launches;
       KDNB_CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
       const int rc = one_step(c, dt);
@@ -537,6 +559,7 @@ int kdnb_host_shard_range(uint64_t total, int rank, int world_size, uint64_t* fi
 int kdnb_upload_particles_sharded(kdnb_ctx* ctx, const kdnb_particle* shard, uint64_t total) {
   CTX_OR_FAIL(ctx);
   if (c->world <= 1) return kdnb_upload_particles(ctx, shard, total);
+  if (total == 0) return upload_empty(c);
   if (!shard) return c->fail(KDNB_E_INVALID, "null particle array");
   if (int rc = plan(c, total)) return rc;
   const uint64_t s = host_shard(total, c->world);
@@ -551,8 +574,9 @@ int kdnb_upload_particles_sharded(kdnb_ctx* ctx, const kdnb_particle* shard, uin
 
 int kdnb_download_particles_sharded(kdnb_ctx* ctx, kdnb_particle* shard_out) {
   CTX_OR_FAIL(ctx);
+  NEED_PARTICLES(c);
+  if (c->empty) return 0;
   if (!shard_out) return c->fail(KDNB_E_INVALID, "null output array");
-  if (c->n == 0) return c->fail(KDNB_E_INVALID, "no particles uploaded");
   uint64_t first = 0, cnt = 0;
   kdnb_host_shard_range(c->n, c->rank_id, c->world, &first, &cnt);
   if (int rc = soa_to_aos(c)) return rc;  // every replica holds the full, bit-identical state
@@ -596,8 +620,9 @@ int kdnb_synchronize(kdnb_ctx* ctx) {
 
 int kdnb_download_accel(kdnb_ctx* ctx, double* acc) {
   CTX_OR_FAIL(ctx);
+  NEED_PARTICLES(c);
+  if (c->empty) return 0;
   if (!acc) return c->fail(KDNB_E_INVALID, "null output array");
-  if (c->n == 0) return c->fail(KDNB_E_INVALID, "no particles uploaded");
   if (!c->tree_valid) {
     // before any build (or after a kick) the reference's acc vector is all zeros (:624-627, :659-661)
     memset(acc, 0, 3 * c->n * sizeof(double));
@@ -611,8 +636,12 @@ int kdnb_download_accel(kdnb_ctx* ctx, double* acc) {
 
 int kdnb_upload_accel(kdnb_ctx* ctx, const double* acc) {
   CTX_OR_FAIL(ctx);
-  if (!acc) return c->fail(KDNB_E_INVALID, "null input array");
   if (!c->tree_valid) return c->fail(KDNB_E_INVALID, "kdnb_upload_accel needs a built tree (particle->slot map)");
+  if (c->empty) {
+    c->acc_valid = true;
+    return 0;
+  }
+  if (!acc) return c->fail(KDNB_E_INVALID, "null input array");
   KDNB_CUDA_TRY(c, cudaMemcpyAsync(c->tmp3, acc, 3 * c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   if (int rc = scatter_acc(c, c->tmp3)) return rc;
   c->acc_valid = true;
@@ -623,6 +652,14 @@ int kdnb_download_tree(kdnb_ctx* ctx, kdnb_node* nodes, uint64_t cap, uint64_t* 
   CTX_OR_FAIL(ctx);
   if (!c->tree_valid) return c->fail(KDNB_E_INVALID, "no tree built for the current positions");
   if (n_nodes) *n_nodes = c->n_nodes;
+  if (c->empty) {  // allocate_node_vec(0) is one node; the build wrote it as an empty leaf (array_kd_tree.rs:524-529)
+    if (nodes) {
+      if (cap < 1) return c->fail(KDNB_E_CAPACITY, "node array smaller than kdnb_node_count()");
+      memset(&nodes[0], 0, sizeof(kdnb_node));
+      nodes[0].kind = KDNB_LEAF;
+    }
+    return 0;
+  }
   if (nodes) {
     if (cap < c->n_nodes) return c->fail(KDNB_E_CAPACITY, "node array smaller than kdnb_node_count()");
     kdnb_node* dev = reinterpret_cast<kdnb_node*>(c->aos);  // staging buffer is sized for this in plan()
@@ -631,9 +668,17 @@ int kdnb_download_tree(kdnb_ctx* ctx, kdnb_node* nodes, uint64_t cap, uint64_t* 
   }
   KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   if (indices) {
-    std::vector<uint32_t> tmp(c->n);
-    KDNB_CUDA_TRY(c, cudaMemcpy(tmp.data(), c->perm, c->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    for (uint64_t i = 0; i < c->n; ++i) indices[i] = tmp[i];
+    // the device holds u32 slots; land them in the upper half of the caller's u64 array and widen front to back in
+    // place (entry i is written over bytes [8i, 8i+8), which lie at or below its own packed source at byte 4n + 4i
+    // and strictly below every packed word still to be read), so no host staging buffer is needed at any N
+    unsigned char* bytes = reinterpret_cast<unsigned char*>(indices);
+    KDNB_CUDA_TRY(c, cudaMemcpy(bytes + 4 * c->n, c->perm, c->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < c->n; ++i) {
+      uint32_t v;
+      memcpy(&v, bytes + 4 * c->n + 4 * i, sizeof v);
+      const uint64_t w = v;
+      memcpy(bytes + 8 * i, &w, sizeof w);
+    }
   }
   return 0;
 }
@@ -642,6 +687,7 @@ int kdnb_download_walk_counts(kdnb_ctx* ctx, uint64_t* counts) {
   CTX_OR_FAIL(ctx);
   if (!(c->flags & KDNB_FLAG_WALK_COUNTS)) return c->fail(KDNB_E_INVALID, "context was created without KDNB_FLAG_WALK_COUNTS");
   if (!c->acc_valid || !c->tree_valid) return c->fail(KDNB_E_INVALID, "no walk results for the current tree");
+  if (c->empty) return 0;
   unsigned long long* dev = reinterpret_cast<unsigned long long*>(c->tmp3);
   if (int rc = gather_counts(c, dev)) return rc;
   KDNB_CUDA_TRY(c, cudaMemcpyAsync(counts, dev, 4 * c->n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
@@ -679,7 +725,14 @@ int kdnb_comm_unique_id(void* id_out) {
 
 int kdnb_comm_init(kdnb_ctx* ctx, const void* id_bytes, int rank, int world_size) {
   CTX_OR_FAIL(ctx);
-  if (world_size < 1 || rank < 0 || rank >= world_size || world_size > 64) return c->fail(KDNB_E_INVALID, "bad rank / world size");
+  if (world_size < 1 || rank < 0 || rank >= world_size || world_size > KDNB_MAX_WORLD) return c->fail(KDNB_E_INVALID, "bad rank / world size");
+  if (c->nccl_comm) {  // joining again (another communicator or world size): leave the previous one first
+    KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    drop_graph_if_any(c);
+    close_peers(c);
+    if (g_nccl.comm_destroy) g_nccl.comm_destroy(c->nccl_comm);
+    c->nccl_comm = nullptr;
+  }
   if (world_size == 1) {
     c->rank_id = 0;
     c->world = 1;

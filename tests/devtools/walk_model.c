@@ -12,7 +12,7 @@
 
 typedef struct {
   double batches, popped, farn, nearn, mixed, leaves, entries, lanes, mixed_rounds, mixed_round_nodes, leaf_rounds,
-      leaf_round_nodes, max_sp, max_pend, drains, part_entries, tests, pack2, pack4, pack32, hist[33];
+      leaf_round_nodes, max_sp, max_pend, drains, part_entries, tests, pack2, pack4, pack32, hist[33], tl[24], sw[16];
 } wm_stats;
 
 static inline int popc(uint32_t x) { return __builtin_popcount(x); }
@@ -30,6 +30,77 @@ static int pack(const uint32_t* m, int n, int K) {
 static void packstats(wm_stats* o, const uint32_t* m, int n, int rep) {
   o->pack2 += rep * pack(m, n, 2); o->pack4 += rep * pack(m, n, 4); o->pack32 += rep * pack(m, n, 32);
   for (int i = 0; i < n; ++i) if (m[i]) o->hist[popc(m[i])] += rep;
+}
+
+
+// ---- two-list drain model: entries with popc(mask) >= T go to a dense list drained by the broadcast loop (one
+// iteration per entry), the others to a sparse list drained lane-privately (rounds = max over lanes of the lane's
+// items in the batch).  tl[3*c+0] = dense iterations, tl[3*c+1] = sparse rounds, tl[3*c+2] = sparse drains, for the
+// (T, sparse capacity) configurations below.
+static const int TL_T[8] = {33, 24, 28, 30, 28, 28, 32, 28};
+static const int TL_CAP[8] = {96, 96, 96, 96, 64, 128, 96, 192};
+typedef struct { int nd, ns; int col[32]; } tl_state;
+static tl_state g_tl[8];
+static void tl_flush_sparse(wm_stats* o, int c) {
+  tl_state* t = &g_tl[c];
+  if (!t->ns) return;
+  int mx = 0;
+  for (int l = 0; l < 32; ++l) { if (t->col[l] > mx) mx = t->col[l]; t->col[l] = 0; }
+  o->tl[3 * c + 1] += mx;
+  o->tl[3 * c + 2] += 1;
+  t->ns = 0;
+}
+static void sw_emit(wm_stats* o, uint32_t m);
+static void tl_emit(wm_stats* o, uint32_t m) {
+  if (!m) return;
+  sw_emit(o, m);
+  for (int c = 0; c < 8; ++c) {
+    tl_state* t = &g_tl[c];
+    if (popc(m) >= TL_T[c]) {
+      o->tl[3 * c + 0] += 1;
+    } else {
+      if (t->ns == TL_CAP[c]) tl_flush_sparse(o, c);
+      t->ns++;
+      for (int l = 0; l < 32; ++l) t->col[l] += (m >> l) & 1;
+    }
+  }
+}
+static void tl_end_group(wm_stats* o) { for (int c = 0; c < 8; ++c) tl_flush_sparse(o, c); }
+
+
+// ---- sliding-window model: entries with popc < T enter a ring of W entries; every lane keeps the bit column of its
+// pending items; a round lets every lane with a non-empty column consume its OLDEST item.  Rounds run only when the
+// ring needs room (until the oldest entries are consumed by every lane) and at the end of the group.
+// sw[2*c] = dense iterations, sw[2*c+1] = rounds.
+static const int SW_T[8] = {33, 33, 33, 28, 28, 28, 24, 33};
+static const int SW_W[8] = {64, 96, 128, 64, 96, 128, 64, 256};
+typedef struct { int head, cnt; uint32_t m[256]; } sw_state;  // m[slot] = lanes that still have to consume it
+static sw_state g_sw[8];
+static void sw_round(wm_stats* o, int c) {
+  sw_state* t = &g_sw[c];
+  const int W = SW_W[c];
+  uint32_t done = 0;  // lanes that consumed an item this round
+  for (int k = 0; k < t->cnt && done != 0xffffffffu; ++k) {
+    const int s = (t->head + k) % W;
+    const uint32_t take = t->m[s] & ~done;
+    t->m[s] &= ~take;
+    done |= take;
+  }
+  o->sw[2 * c + 1] += 1;
+  while (t->cnt && !t->m[t->head]) t->head = (t->head + 1) % W, t->cnt--;
+}
+static void sw_emit(wm_stats* o, uint32_t m) {
+  if (!m) return;
+  for (int c = 0; c < 8; ++c) {
+    sw_state* t = &g_sw[c];
+    if (popc(m) >= SW_T[c]) { o->sw[2 * c] += 1; continue; }
+    while (t->cnt == SW_W[c]) sw_round(o, c);
+    t->m[(t->head + t->cnt) % SW_W[c]] = m;
+    t->cnt++;
+  }
+}
+static void sw_end_group(wm_stats* o) {
+  for (int c = 0; c < 8; ++c) { while (g_sw[c].cnt) sw_round(o, c); g_sw[c].head = 0; }
 }
 
 // group = 32 consecutive tree slots starting at base; slot -> particle id through idx[]
@@ -82,6 +153,7 @@ void wm_run(const okd_node* nodes, const okd_particle* parts, const uint64_t* id
             adds++;
             out->entries++;
             out->lanes += popc(am);
+            tl_emit(out, am);
           }
           const uint32_t ms = mk & ~am;
           if (ms) {
@@ -118,6 +190,7 @@ void wm_run(const okd_node* nodes, const okd_particle* parts, const uint64_t* id
               out->part_entries++;
               out->lanes += popc(m);
               lms[i] = m;
+              tl_emit(out, m);
             }
           }
           packstats(out, lms, r, 1);
@@ -153,6 +226,7 @@ void wm_run(const okd_node* nodes, const okd_particle* parts, const uint64_t* id
                 if (base + l < n && idx[base + l] == pid) m &= ~(1u << l);
               out->entries++, out->part_entries++;
               out->lanes += popc(m);
+              tl_emit(out, m);
             }
             if (list + (int)q->u.leaf.num_parts > 64) out->drains++, list = 0;
             list += (int)q->u.leaf.num_parts;
@@ -172,6 +246,7 @@ void wm_run(const okd_node* nodes, const okd_particle* parts, const uint64_t* id
           adds++;
           out->entries++;
           out->lanes += popc(mk);
+          tl_emit(out, mk);
         } else if (size2 >= theta2 * dmax2 * (1 + 1e-9)) {
           out->nearn++;
           newn[nn] = (uint32_t)q->u.in.right, newm[nn] = mk, nn++;
@@ -191,6 +266,7 @@ void wm_run(const okd_node* nodes, const okd_particle* parts, const uint64_t* id
             if (am) {
               out->entries++;
               out->lanes += popc(am);
+              tl_emit(out, am);
               if (list + 1 > 64) out->drains++, list = 0;
               list++;
             }
@@ -209,6 +285,8 @@ void wm_run(const okd_node* nodes, const okd_particle* parts, const uint64_t* id
       if (sp > out->max_sp) out->max_sp = sp;
       if (pend > out->max_pend) out->max_pend = pend;
     }
+    tl_end_group(out);
+    sw_end_group(out);
   }
   free(snode);
   free(smask);

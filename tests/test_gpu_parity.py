@@ -399,6 +399,40 @@ def test_reference_api_mirror(orc):
     assert last == 0 and nodes[0]["kind"] == kd.LEAF and nodes[0]["num_parts"] == 2
 
 
+def test_empty_bodies_are_a_no_op_like_the_reference(orc):
+    """`simple_sim(&mut vec![], dt, steps)` does not panic in the reference: acc / indices are empty, the tree is the
+    one node of allocate_node_vec(0) (array_kd_tree.rs:45-60) which the build writes as Leaf{0, [0; MAX_PARTS]}
+    (:524-529), and every stage loops over nothing."""
+    empty = np.zeros(0, kd.PARTICLE)
+    onodes, oidx, olast = orc.build_tree_canonical(np.zeros(0, PARTICLE))
+    assert len(onodes) == 1 and olast == 0 and not onodes[0]["is_internal"] and onodes[0]["num_parts"] == 0
+    with kd.KDTreeSim(flags=kd.FLAG_WALK_COUNTS) as sim:
+        sim.upload(empty)
+        assert sim.count == 0 and sim.node_count == 1
+        with pytest.raises(kd.KdnbError):
+            sim.calc_accel()                     # call order is still checked
+        sim.build_tree()
+        nodes, idx = sim.tree()
+        assert len(nodes) == 1 and len(idx) == 0
+        assert nodes[0]["kind"] == kd.LEAF and nodes[0]["num_parts"] == 0
+        assert np.array_equal(kd.leaf_parts(nodes, idx)[0], onodes[0]["leaf_parts"])   # 0 padding, not usize::MAX
+        sim.calc_accel()
+        assert sim.accel().shape == (0, 3) and sim.walk_counts().shape == (0, 4)
+        sim.kick_drift(1e-3)
+        sim.simple_sim(1e-3, 5)
+        assert len(sim.download()) == 0
+        # the context is reusable afterwards, and an empty upload after a real one resets it
+        parts = kd.circular_orbits(100)
+        sim.upload(parts)
+        sim.build_tree()
+        assert sim.count == 101 and sim.node_count == kd.nodes_needed_for_particles(101)
+        sim.upload(empty)
+        assert sim.count == 0 and sim.node_count == 1
+        with pytest.raises(kd.KdnbError):
+            sim.calc_accel()                     # the tree of the previous upload is gone
+    kd.simple_sim(empty, 1e-3, 3)                # the one-call form
+
+
 def test_error_codes_instead_of_panics():
     with kd.KDTreeSim() as sim:
         with pytest.raises(kd.KdnbError):
