@@ -72,7 +72,11 @@ enum {
   KDNB_FLAG_PROFILE = 1u,     /* record CUDA events around build / walk / kick / exchange */
   KDNB_FLAG_WALK_COUNTS = 2u, /* walk also counts node tests / accepts / leaf visits / pair interactions per particle */
   KDNB_FLAG_EXACT_MATH = 4u   /* force magnitudes with IEEE sqrt and divide exactly as the reference writes them
-                                 (default: rsqrt-based, <= 2 ulp apart; acceptance tests are always exact) */
+                                 (default: rsqrt-based, <= 2 ulp apart; acceptance tests are always exact).
+                                 Where a squared pair distance is 0 or underflows to 0 (coincident particles,
+                                 separations below ~1e-154) the reference divides by zero and its acceleration is
+                                 non-finite; the default path is non-finite for exactly the same particles but may
+                                 hold NaN where the reference holds +-inf — with this flag the values are identical */
 };
 
 typedef struct kdnb_config {
