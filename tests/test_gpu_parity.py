@@ -399,6 +399,49 @@ def test_reference_api_mirror(orc):
     assert last == 0 and nodes[0]["kind"] == kd.LEAF and nodes[0]["num_parts"] == 2
 
 
+def _degenerate(kind, n, seed):
+    """Geometries that collapse one or two dimensions or put many particles on exactly equal coordinates."""
+    rng = np.random.default_rng(seed)
+    parts = cube(n, seed=seed, equal_mass=False)
+    p = parts["p"].copy()
+    if kind == "line_x":            # collinear along x: y and z lists are flat
+        p[:, 1:] = 0.5
+    elif kind == "line_diag":       # collinear along the diagonal: three identical orders, widest-axis ties
+        p[:, 1] = p[:, 0]
+        p[:, 2] = p[:, 0]
+    elif kind == "flat_x":          # the x extent is 0: dimension 0 is never the widest
+        p[:, 0] = -0.25
+    elif kind == "flat_y":
+        p[:, 1] = 0.0
+    elif kind == "grid":            # integer lattice: every coordinate value shared by ~n^(2/3) particles
+        g = max(1, int(round(n ** (1 / 3))))
+        ids = rng.permutation(n)
+        p = np.stack([ids % g, (ids // g) % g, ids // (g * g)], axis=1).astype(np.float64)
+    parts["p"] = p
+    return parts
+
+
+@pytest.mark.parametrize("kind", ["line_x", "line_diag", "flat_x", "flat_y", "grid"])
+@pytest.mark.parametrize("mp,layout", [(8, kd.LAYOUT_PADDED), (7, kd.LAYOUT_DENSE)])
+def test_degenerate_geometries_tree_and_walk(orc, kind, mp, layout):
+    parts = _degenerate(kind, 3000, seed=21)
+    olayout = O_PADDED if layout == kd.LAYOUT_PADDED else O_DENSE
+    with kd.KDTreeSim(max_parts=mp, layout=layout, flags=kd.FLAG_WALK_COUNTS) as sim:
+        sim.upload(parts)
+        sim.build_tree()
+        gnodes, gidx = sim.tree()
+        sim.calc_accel()
+        acc, cnt = sim.accel(), sim.walk_counts()
+    onodes, oidx, _ = orc.build_tree_canonical(parts, max_parts=mp, layout=olayout)
+    assert_tree_bit_exact(orc, gnodes, gidx, onodes, oidx, mp)
+    oacc, ocnt = orc.calc_accel_all(parts, to_oracle_nodes(orc, gnodes, gidx, mp), counts=True)
+    for k, f in enumerate(("node_visits", "accepts", "leaf_visits", "pp")):
+        assert np.array_equal(cnt[:, k], ocnt[f]), f
+    # On a line or a lattice the pulls from both sides nearly cancel (|sum| down to 1e-4 of the sum of |terms|), so the
+    # summation-order difference (running sum here, pairwise in the reference) shows at 1e-11; decisions are exact.
+    assert np.isfinite(acc).all() and rel_err(acc, oacc).max() <= 1e-9
+
+
 def test_empty_bodies_are_a_no_op_like_the_reference(orc):
     """`simple_sim(&mut vec![], dt, steps)` does not panic in the reference: acc / indices are empty, the tree is the
     one node of allocate_node_vec(0) (array_kd_tree.rs:45-60) which the build writes as Leaf{0, [0; MAX_PARTS]}

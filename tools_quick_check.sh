@@ -6,7 +6,7 @@ TAG=${1:-quick}
 mkdir -p gpurun_out
 t0=$SECONDS
 timeout 50 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -p no:cacheprovider \
-  -k "empty_bodies or error_codes or (build_padded and 2049) or (build_dense and 5001) or (walk_ring and 5000) or (production_kernel and ring) or kick_drift or (simple_sim_trajectory and 1000-100) or reference_api_mirror or graph_replay_equals" \
+  -k "empty_bodies or degenerate or error_codes or (build_padded and 2049) or (build_dense and 5001) or (walk_ring and 5000) or (production_kernel and ring) or kick_drift or (simple_sim_trajectory and 1000-100) or reference_api_mirror or graph_replay_equals" \
   > gpurun_out/pytest_quick_${TAG}.log 2>&1
 echo "pytest rc=$? $((SECONDS - t0)) s"; tail -n 3 gpurun_out/pytest_quick_${TAG}.log
 timeout 55 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_quick_${TAG}.log 2>&1
