@@ -130,7 +130,7 @@ inline std::vector<std::array<double, 3>> calc_accel_all(const std::vector<Parti
   c.check(kdnb_build_tree(c.get()), "kdnb_build_tree");
   c.check(kdnb_calc_accel(c.get()), "kdnb_calc_accel");
   std::vector<std::array<double, 3>> acc(particles.size());
-  c.check(kdnb_download_accel(c.get(), &acc[0][0]), "kdnb_download_accel");
+  c.check(kdnb_download_accel(c.get(), reinterpret_cast<double*>(acc.data())), "kdnb_download_accel");  // (empty: no-op)
   return acc;
 }
 
