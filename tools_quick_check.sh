@@ -1,13 +1,16 @@
 #!/bin/bash
-# usage (under gpurun, one GPU, ~90 s): bash tools_quick_check.sh <tag>
+# usage (under gpurun, one GPU, ~100 s): bash tools_quick_check.sh <tag>
 # The shortest round-end sanity of a rebuilt libkdnb.so: a cross-section of the GPU parity suite (tree bit-exact,
-# walk decisions, kick/drift, trajectory, error codes, empty input), then one short default bench line.
+# walk decisions, kick/drift, trajectory, error codes, empty and degenerate inputs), the walk register-budget A/B on
+# shard-sized grids (tools/ab_walk_minb.py), then one short default bench line.
 TAG=${1:-quick}
 mkdir -p gpurun_out
 t0=$SECONDS
-timeout 50 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -p no:cacheprovider \
+timeout 40 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -p no:cacheprovider \
   -k "empty_bodies or degenerate or error_codes or (build_padded and 2049) or (build_dense and 5001) or (walk_ring and 5000) or (production_kernel and ring) or kick_drift or (simple_sim_trajectory and 1000-100) or reference_api_mirror or graph_replay_equals" \
   > gpurun_out/pytest_quick_${TAG}.log 2>&1
 echo "pytest rc=$? $((SECONDS - t0)) s"; tail -n 3 gpurun_out/pytest_quick_${TAG}.log
-timeout 55 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_quick_${TAG}.log 2>&1
+timeout 45 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_quick_${TAG}.log 2>&1
 echo "bench rc=$? $((SECONDS - t0)) s"; grep '^{' gpurun_out/bench_quick_${TAG}.log | cut -c1-600
+timeout 35 python tools/ab_walk_minb.py gpurun_out/ab_walk_minb_${TAG}.txt 2>&1 | tail -n 8
+echo "ab rc=$? $((SECONDS - t0)) s"
