@@ -2,7 +2,6 @@
 // (Parallel/RustVersion/src/array_kd_tree.rs:585-621) with calc_pp_accel (array_particle.rs:67-76) in the leaves:
 // host-side launch logic, the peer-exchange wait kernel, and the kernels themselves (walk_legacy.cuh).
 #include <algorithm>
-#include <cmath>
 #include <cstdlib>
 
 #include "ctx.cuh"
@@ -60,26 +59,6 @@ static void launch_walk(Ctx* c, uint32_t begin, uint32_t end) {
 #undef KDNB_WALK_ARGS
 }
 
-// Register budget of the production walk: 24 one-warp CTAs per SM at 80 registers (no spills), or 32 at 64 registers
-// (1.4 % more instructions).  The kernel is issue-bound, so a wave of R CTAs per SM takes ceil(R / 4) CTA-times (four
-// schedulers per SM) — but a scheduler needs about 3.5 resident warps to keep its issue port busy, so a last wave of
-// only a few hundred CTAs still costs ~3.5 CTA-times.  With 31251 CTAs (N = 1M on one GPU) that tail is noise and 24
-// wins; the 3906 CTAs of a 1/8 shard are 1.1 waves of 24 per SM but ONE wave of 32, 7.1 instead of 9.5 CTA-times.
-// The model reproduces the measured walk times of profiles/README.md at 1, 2, 4 and 8 GPUs to within 1.5 CTA-times
-// (2.22 / 1.21 / 0.71 / 0.43 ms at N = 1M with 24 per SM: 53 / 27.5 / 15.5 / 9.5 CTA-times of 42 us) but not the
-// single partial wave of N = 100k (10 measured against 6), so it stays opt-in (KDNB_WALK_MINB=auto) until the
-// 32-per-SM launch has been timed on a shard-sized grid.
-static int pick_minb(uint32_t grid, int num_sms) {
-  auto cost = [&](int r, double per_cta) {
-    const uint64_t slots = (uint64_t)num_sms * r;
-    const uint64_t full = grid / slots, rem = grid % slots;
-    double t = (double)full * (r / 4);
-    if (rem) t += std::max(3.5, std::ceil((double)rem / (4.0 * num_sms)));
-    return t * per_cta;
-  };
-  return cost(32, 1.014) < cost(24, 1.0) ? 32 : 24;
-}
-
 static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
   const uint32_t grid = (end - begin + 31) / 32;
   const bool counts = (c->flags & KDNB_FLAG_WALK_COUNTS) != 0;
@@ -88,7 +67,16 @@ static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
   if (!c->p2p_on) pp.world = 0;
   int lshift = 0;  // lanes per leaf in the leaf rounds: the smallest power of two >= MAX_PARTS
   while ((1u << lshift) < c->mp) ++lshift;
-#define KDNB_WALK_ARGS c->nodes, c->posm, c->acc_t, begin, end, c->theta2, c->wcounts, pp, c->flat, lshift
+  // Prefetches (bit 0: the right child's record when a node is opened; bit 1: a leaf's particles when it is
+  // classified): a few more instructions per batch, which cost where the kernel is issue-bound (many waves) and pay
+  // where it is latency-bound (the last warps of a launch: small grids, i.e. multi-GPU shards and N <= ~250k).
+  // KDNB_WALK_PF=<mask> overrides.
+  static const int pf_forced = [] {
+    const char* s = getenv("KDNB_WALK_PF");
+    return s ? atoi(s) : -1;
+  }();
+  const int prefetch = pf_forced >= 0 ? pf_forced : (grid < 5u * 24u * (uint32_t)c->num_sms / 2u ? 3 : 0);
+#define KDNB_WALK_ARGS c->nodes, c->posm, c->acc_t, begin, end, c->theta2, c->wcounts, pp, c->flat, lshift, prefetch
   const bool peer = pp.world > 1;
   if (exact && counts)
     KDNB_LAUNCH(c, (walk2_kernel<true, true, true, 1>), grid, 32, 0, KDNB_WALK_ARGS);
@@ -96,19 +84,19 @@ static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
     KDNB_LAUNCH(c, (walk2_kernel<true, false, true, 1>), grid, 32, 0, KDNB_WALK_ARGS);
   else if (counts)
     KDNB_LAUNCH(c, (walk2_kernel<false, true, true, 1>), grid, 32, 0, KDNB_WALK_ARGS);
+  else if (peer)
+    KDNB_LAUNCH(c, (walk2_kernel<false, false, true, 24>), grid, 32, 0, KDNB_WALK_ARGS);
   else {
-    static const int forced = [] {
-      const char* s = getenv("KDNB_WALK_MINB");  // 24 (default) or 32 CTAs per SM; "auto" = pick_minb() per launch
-      return s ? (s[0] == 'a' ? -1 : atoi(s)) : 24;
+    static const int minb = [] {
+      const char* s = getenv("KDNB_WALK_MINB");  // profiling knob: CTAs per SM the register budget is sized for
+      return s ? atoi(s) : 24;
     }();
-    const int minb = forced < 0 ? pick_minb(grid, c->num_sms) : forced;
-    if (peer) {
-      if (minb == 32) KDNB_LAUNCH(c, (walk2_kernel<false, false, true, 32>), grid, 32, 0, KDNB_WALK_ARGS);
-      else KDNB_LAUNCH(c, (walk2_kernel<false, false, true, 24>), grid, 32, 0, KDNB_WALK_ARGS);
-    } else {
-      if (minb == 32) KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 32>), grid, 32, 0, KDNB_WALK_ARGS);
-      else KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 24>), grid, 32, 0, KDNB_WALK_ARGS);
-    }
+    // 24 one-warp CTAs per SM = 80 registers, no spills.  32 per SM at 64 registers is slower at every grid size, also
+    // where it would turn 1.1 waves into one (shard-sized grids: 0.394 against 0.374 ms at 3907 CTAs, 2.265 against
+    // 2.219 ms at 31251; profiles/r01_ab_walk_minb.txt) — the tail of the kernel is bound by the latency of the
+    // last warps, not by the number of waves.
+    if (minb == 32) KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 32>), grid, 32, 0, KDNB_WALK_ARGS);
+    else KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 24>), grid, 32, 0, KDNB_WALK_ARGS);
   }
 #undef KDNB_WALK_ARGS
 }

@@ -1,6 +1,6 @@
-"""A/B of the walk's register budget on shard-sized grids (one GPU): walk ms per step for 24 and 32 one-warp CTAs
-per SM (KDNB_WALK_MINB) at sizes whose grid equals a 1/8, 1/4, 1/2 shard of N=1M, plus N=100k and N=1M.
-usage (GPU box): python tools/ab_walk_minb.py [out.txt]        — one child process per setting (the knob is read once)"""
+"""A/B of a walk launch knob on shard-sized grids (one GPU): walk ms per step for each value of an environment variable
+(KDNB_WALK_MINB 24 32, KDNB_WALK_PF 0 1, ...) at sizes whose grid equals a 1/8, 1/4, 1/2 shard of N=1M, plus N=100k and N=1M.
+usage (GPU box): python tools/ab_walk_env.py VAR value [value ...] [--out file]   — one child process per setting"""
 import os
 import subprocess
 import sys
@@ -26,14 +26,21 @@ with kd.KDTreeSim(flags=kd.FLAG_PROFILE) as sim:
 
 
 def main():
-    out = open(sys.argv[1], "w") if len(sys.argv) > 1 else None
-    for n in (125_000, 250_000, 500_000, 100_000, 1_000_000):
+    args = sys.argv[1:]
+    out = None
+    if "--out" in args:
+        k = args.index("--out")
+        out = open(args[k + 1], "w")
+        del args[k:k + 2]
+    var, values = args[0], args[1:]
+    sizes = [int(x) for x in os.environ.get("AB_SIZES", "125000 250000 500000 100000 1000000").split()]
+    for n in sizes:
         row = []
-        for minb in ("24", "32"):
+        for val in values:
             r = subprocess.run([sys.executable, "-c", CHILD, str(n)], capture_output=True, text=True,
-                               env={**os.environ, "KDNB_WALK_MINB": minb}, timeout=120)
+                               env={**os.environ, var: val}, timeout=120)
             row.append(r.stdout.strip().split()[0] if r.returncode == 0 and r.stdout.strip() else "ERR:" + r.stderr[-200:])
-        line = f"N={n:8d} grid={(n + 32) // 32:6d}  walk ms/step  minb24 {row[0]}  minb32 {row[1]}"
+        line = f"N={n:8d} grid={(n + 32) // 32:6d}  walk ms/step  " + "  ".join(f"{var}={v} {t}" for v, t in zip(values, row))
         print(line, flush=True)
         if out:
             out.write(line + "\n")

@@ -1,8 +1,8 @@
 #!/bin/bash
 # usage (under gpurun, one GPU, ~100 s): bash tools_quick_check.sh <tag>
 # The shortest round-end sanity of a rebuilt libkdnb.so: a cross-section of the GPU parity suite (tree bit-exact,
-# walk decisions, kick/drift, trajectory, error codes, empty and degenerate inputs), the walk register-budget A/B on
-# shard-sized grids (tools/ab_walk_minb.py), then one short default bench line.
+# walk decisions, kick/drift, trajectory, error codes, empty and degenerate inputs), one short default bench line,
+# then an A/B of one walk launch knob on shard-sized grids (tools/ab_walk_env.py; AB_VAR / AB_VALUES).
 TAG=${1:-quick}
 mkdir -p gpurun_out
 t0=$SECONDS
@@ -12,5 +12,5 @@ timeout 40 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -p no:cachepro
 echo "pytest rc=$? $((SECONDS - t0)) s"; tail -n 3 gpurun_out/pytest_quick_${TAG}.log
 timeout 45 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_quick_${TAG}.log 2>&1
 echo "bench rc=$? $((SECONDS - t0)) s"; grep '^{' gpurun_out/bench_quick_${TAG}.log | cut -c1-600
-timeout 35 python tools/ab_walk_minb.py gpurun_out/ab_walk_minb_${TAG}.txt 2>&1 | tail -n 8
+AB_SIZES=${AB_SIZES:-"125000 250000 1000000"} timeout 35 python tools/ab_walk_env.py ${AB_VAR:-KDNB_WALK_PF} ${AB_VALUES:-0 1 3} --out gpurun_out/ab_walk_${TAG}.txt 2>&1 | tail -n 8
 echo "ab rc=$? $((SECONDS - t0)) s"
