@@ -67,15 +67,6 @@ __device__ __forceinline__ double rsqrt_estimate(double x) {
 #endif
 }
 
-// hint: bring the line holding *p towards the SM (no architectural effect)
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-#ifndef KDNB_SIMT
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-  (void)p;
-#endif
-}
-
 // ---- order-preserving key of an f64 coordinate (canonical order: -0.0 == +0.0, ties by index)
 __host__ __device__ inline uint64_t f64_key(double x) {
   x = x + 0.0;  // -0.0 -> +0.0 (round-to-nearest)

@@ -1,7 +1,6 @@
 // walk.cu — theta-criterion force walk, calc_accel / accel_recur of the reference
 // (Parallel/RustVersion/src/array_kd_tree.rs:585-621) with calc_pp_accel (array_particle.rs:67-76) in the leaves:
 // host-side launch logic, the peer-exchange wait kernel, and the kernels themselves (walk_legacy.cuh).
-#include <algorithm>
 #include <cstdlib>
 
 #include "ctx.cuh"
@@ -67,16 +66,7 @@ static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
   if (!c->p2p_on) pp.world = 0;
   int lshift = 0;  // lanes per leaf in the leaf rounds: the smallest power of two >= MAX_PARTS
   while ((1u << lshift) < c->mp) ++lshift;
-  // Prefetches (bit 0: the right child's record when a node is opened; bit 1: a leaf's particles when it is
-  // classified): a few more instructions per batch, which cost where the kernel is issue-bound (many waves) and pay
-  // where it is latency-bound (the last warps of a launch: small grids, i.e. multi-GPU shards and N <= ~250k).
-  // KDNB_WALK_PF=<mask> overrides.
-  static const int pf_forced = [] {
-    const char* s = getenv("KDNB_WALK_PF");
-    return s ? atoi(s) : -1;
-  }();
-  const int prefetch = pf_forced >= 0 ? pf_forced : (grid < 5u * 24u * (uint32_t)c->num_sms / 2u ? 3 : 0);
-#define KDNB_WALK_ARGS c->nodes, c->posm, c->acc_t, begin, end, c->theta2, c->wcounts, pp, c->flat, lshift, prefetch
+#define KDNB_WALK_ARGS c->nodes, c->posm, c->acc_t, begin, end, c->theta2, c->wcounts, pp, c->flat, lshift
   const bool peer = pp.world > 1;
   if (exact && counts)
     KDNB_LAUNCH(c, (walk2_kernel<true, true, true, 1>), grid, 32, 0, KDNB_WALK_ARGS);
@@ -93,8 +83,9 @@ static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
     }();
     // 24 one-warp CTAs per SM = 80 registers, no spills.  32 per SM at 64 registers is slower at every grid size, also
     // where it would turn 1.1 waves into one (shard-sized grids: 0.394 against 0.374 ms at 3907 CTAs, 2.265 against
-    // 2.219 ms at 31251; profiles/r01_ab_walk_minb.txt) — the tail of the kernel is bound by the latency of the
-    // last warps, not by the number of waves.
+    // 2.219 ms at 31251; profiles/r01_ab_walk_minb.txt) — the ~0.12 ms a launch takes beyond its issue-slot work is
+    // not a matter of waves; nor of node / leaf load latency: prefetching the right child at push time and a leaf's
+    // particles at classification made every size ~1 % slower (profiles/r01_ab_walk_prefetch.txt).
     if (minb == 32) KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 32>), grid, 32, 0, KDNB_WALK_ARGS);
     else KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 24>), grid, 32, 0, KDNB_WALK_ARGS);
   }

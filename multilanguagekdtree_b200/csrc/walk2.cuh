@@ -151,8 +151,7 @@ template <bool EXACT, bool COUNTS, bool PEER, bool FLATZ>
 __device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __restrict__ nodes,
                                            const PosM* __restrict__ posm, double* __restrict__ acc_t,
                                            uint32_t slot_begin, uint32_t slot_end, double theta2,
-                                           unsigned long long* __restrict__ wcounts, const P2P& p2p, int lshift,
-                                           int prefetch) {
+                                           unsigned long long* __restrict__ wcounts, const P2P& p2p, int lshift) {
   const int lane = threadIdx.x;
   const uint32_t lt = (1u << lane) - 1u;
   const uint32_t base = slot_begin + blockIdx.x * 32u;
@@ -225,10 +224,6 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __rest
         if (size2 < theta2 * dmin2 * far_margin) kind = W2_FAR;
         else if (size2 >= theta2 * dmax2 * near_margin) kind = W2_NEAR;
       }
-    }
-    if ((prefetch & 2) && kind == W2_LEAF) {  // the leaf's particles are read at the end of this batch (leaf rounds below)
-      prefetch_l1(posm + na);
-      prefetch_l1(posm + na + 4);
     }
     __syncwarp();
     if (COUNTS) {  // every particle in an entry's mask tests that node (and accepts it when it is far)
@@ -307,10 +302,6 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __rest
         S.snode[i + 1] = node + 1;  // left (the next record)
         S.smask[i] = omask;
         S.smask[i + 1] = omask;
-        // the right child's record is far away in the node array (the left one follows its parent): start fetching it
-        // now, it is popped within the next few batches.  Pays only where the kernel is latency-bound — the last
-        // warps of a launch, i.e. small grids (walk.cu decides).
-        if (prefetch & 1) prefetch_l1(nodes + na);
       }
       sp += 2 * __popc(bal);
     }
@@ -405,13 +396,13 @@ template <bool EXACT, bool COUNTS, bool PEER, int MINB>
 __global__ void __launch_bounds__(32, MINB)
 walk2_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, double* __restrict__ acc_t,
              uint32_t slot_begin, uint32_t slot_end, double theta2, unsigned long long* __restrict__ wcounts,
-             P2P p2p, const uint32_t* __restrict__ flat, int lshift, int prefetch) {
+             P2P p2p, const uint32_t* __restrict__ flat, int lshift) {
   pdl_sync();
   __shared__ W2Smem<EXACT> S;
   if (!EXACT && !COUNTS && flat[3])
-    walk2_body<EXACT, COUNTS, PEER, true>(S, nodes, posm, acc_t, slot_begin, slot_end, theta2, wcounts, p2p, lshift, prefetch);
+    walk2_body<EXACT, COUNTS, PEER, true>(S, nodes, posm, acc_t, slot_begin, slot_end, theta2, wcounts, p2p, lshift);
   else
-    walk2_body<EXACT, COUNTS, PEER, false>(S, nodes, posm, acc_t, slot_begin, slot_end, theta2, wcounts, p2p, lshift, prefetch);
+    walk2_body<EXACT, COUNTS, PEER, false>(S, nodes, posm, acc_t, slot_begin, slot_end, theta2, wcounts, p2p, lshift);
 }
 
 }  // namespace kdnb

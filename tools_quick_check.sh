@@ -12,5 +12,6 @@ timeout 40 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -p no:cachepro
 echo "pytest rc=$? $((SECONDS - t0)) s"; tail -n 3 gpurun_out/pytest_quick_${TAG}.log
 timeout 45 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_quick_${TAG}.log 2>&1
 echo "bench rc=$? $((SECONDS - t0)) s"; grep '^{' gpurun_out/bench_quick_${TAG}.log | cut -c1-600
+[ -n "$SKIP_AB" ] && exit 0
 AB_SIZES=${AB_SIZES:-"125000 250000 1000000"} timeout 35 python tools/ab_walk_env.py ${AB_VAR:-KDNB_WALK_PF} ${AB_VALUES:-0 1 3} --out gpurun_out/ab_walk_${TAG}.txt 2>&1 | tail -n 8
 echo "ab rc=$? $((SECONDS - t0)) s"
