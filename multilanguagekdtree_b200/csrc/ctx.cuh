@@ -79,6 +79,10 @@ struct Ctx {
   double* acc_t = nullptr;   // [slots_pad][3] tree-ordered accelerations (the exchanged array)
   unsigned long long* wcounts = nullptr;  // [n][4] optional walk counters, tree order
   double* tmp3 = nullptr;    // [n][3] staging for accel up/download
+  uint32_t* gcost = nullptr;   // [groups] work of every 32-slot group in the last production walk (walk.cu)
+  uint32_t* gorder = nullptr;  // [groups] launch order of the next walk: heaviest group first
+  uint64_t gcost_n = 0;        // particle count / shard the recorded work belongs to (0: none)
+  uint32_t gcost_begin = 0, gcost_end = 0;
   bool tree_valid = false, acc_valid = false, map_valid = false;
   bool bottom_attr_set = false;  // build_bottom's dynamic shared memory limit raised on this context's device
   uint64_t planned_n = 0;

@@ -120,6 +120,9 @@ static void free_all(Ctx* c) {
   fr(c->p2p_state);
   fr(c->wcounts);
   fr(c->tmp3);
+  fr(c->gcost);
+  fr(c->gorder);
+  c->gcost_n = 0;
 }
 
 // ---- peer-memory exchange set-up: cudaIpc handles of acc_t and of the flag array, all-gathered with NCCL
@@ -225,6 +228,7 @@ static uint64_t shard_slots_for(uint64_t n, int world) { return (((n + world - 1
 // (re)plan and (re)allocate for `n` particles
 static int plan(Ctx* c, uint64_t n) {
   if (n > 0x7fffff00ull) return c->fail(KDNB_E_INVALID, "particle count exceeds the 32-bit index range of the device path");
+  if (c->n != n) c->gcost_n = 0;  // (the recorded walk work stays a usable ordering hint for the same particle count)
   c->n = n;
   c->empty = false;
   c->n_nodes = subtree_nodes(n, c->mp, c->layout);
@@ -276,6 +280,8 @@ static int plan(Ctx* c, uint64_t n) {
     if (!rc) rc = dev_alloc(c, &c->p2p_state, 4 + P2P_MAX);
     if (!rc && (c->flags & KDNB_FLAG_WALK_COUNTS)) rc = dev_alloc(c, &c->wcounts, 4 * n);
     if (!rc) rc = dev_alloc(c, &c->tmp3, 4 * n);
+    if (!rc) rc = dev_alloc(c, &c->gcost, n / 32 + 2);
+    if (!rc) rc = dev_alloc(c, &c->gorder, n / 32 + 2);
     if (rc) {
       free_all(c);
       c->cap = c->node_cap = c->table_cap = c->chunk_cap = 0;

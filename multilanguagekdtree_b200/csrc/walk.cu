@@ -66,7 +66,26 @@ static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
   if (!c->p2p_on) pp.world = 0;
   int lshift = 0;  // lanes per leaf in the leaf rounds: the smallest power of two >= MAX_PARTS
   while ((1u << lshift) < c->mp) ++lshift;
-#define KDNB_WALK_ARGS c->nodes, c->posm, c->acc_t, begin, end, c->theta2, c->wcounts, pp, c->flat, lshift
+  // Heaviest-first launch order from the work the groups reported in the previous walk of the same particle set and
+  // shard (the tree order moves little from step to step).  Production kernel only; KDNB_WALK_LPT=0 disables.
+  static const bool lpt = [] {
+    const char* s = getenv("KDNB_WALK_LPT");
+    return s ? atoi(s) != 0 : true;
+  }();
+  const bool production = !exact && !counts;
+  const uint32_t* gorder = nullptr;
+  uint32_t* gcost = nullptr;
+  if (production && lpt) {
+    if (c->gcost_n == c->n && c->gcost_begin == begin && c->gcost_end == end && grid > 1) {
+      KDNB_LAUNCH(c, walk_order_kernel, 1, 1024, 0, c->gcost, c->gorder, grid);
+      gorder = c->gorder;
+    }
+    gcost = c->gcost;
+    c->gcost_n = c->n;
+    c->gcost_begin = begin;
+    c->gcost_end = end;
+  }
+#define KDNB_WALK_ARGS c->nodes, c->posm, c->acc_t, begin, end, c->theta2, c->wcounts, pp, c->flat, lshift, gorder, gcost
   const bool peer = pp.world > 1;
   if (exact && counts)
     KDNB_LAUNCH(c, (walk2_kernel<true, true, true, 1>), grid, 32, 0, KDNB_WALK_ARGS);

@@ -151,10 +151,14 @@ template <bool EXACT, bool COUNTS, bool PEER, bool FLATZ>
 __device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __restrict__ nodes,
                                            const PosM* __restrict__ posm, double* __restrict__ acc_t,
                                            uint32_t slot_begin, uint32_t slot_end, double theta2,
-                                           unsigned long long* __restrict__ wcounts, const P2P& p2p, int lshift) {
+                                           unsigned long long* __restrict__ wcounts, const P2P& p2p, int lshift,
+                                           const uint32_t* __restrict__ gorder, uint32_t* __restrict__ gcost) {
   const int lane = threadIdx.x;
   const uint32_t lt = (1u << lane) - 1u;
-  const uint32_t base = slot_begin + blockIdx.x * 32u;
+  // CTA -> group of 32 tree slots: in launch order, or heaviest first by the previous step's work (walk.cu)
+  const uint32_t group = gorder ? gorder[blockIdx.x] : blockIdx.x;
+  const uint32_t base = slot_begin + group * 32u;
+  uint32_t work = 0;  // drained list entries + 4 per batch: proportional to the issue slots this group used
   const uint32_t slot = base + lane;
   const bool valid_p = slot < slot_end;
   const bool warp_has_work = base < slot_end;
@@ -193,6 +197,7 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __rest
     const int room = W2_STACK - sp;
     const int nb = min(min(sp, 32), max(1, room));
     sp -= nb;
+    work += 4u;
     const bool has = lane < nb;
     uint32_t node = 0, na = 0, nbits = 0, mk = 0;
     int kind = W2_NONE;
@@ -281,6 +286,7 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __rest
         const int add = __popc(bal);
         if (ln + add > W2_LIST) {
           drain2<EXACT, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
+          work += (uint32_t)ln;
           ln = 0;
         }
         if (mine) {
@@ -326,6 +332,7 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __rest
         if (valid) qv = posm[j];
         if (ln + add > W2_LIST) {
           drain2<EXACT, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
+          work += (uint32_t)ln;
           ln = 0;
         }
         if (valid) {
@@ -346,6 +353,8 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __rest
     __syncwarp();
   }
   drain2<EXACT, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
+  work += (uint32_t)ln;
+  if (gcost && lane == 0 && warp_has_work) gcost[group] = work;
 
   // ---- results.  Single GPU / NCCL mode: tree-ordered accelerations into the local acc_t.  Peer mode: the same
   // 24 bytes go straight into EVERY rank's acc_t over NVLink (this rank's shard of everyone's copy), followed by a
@@ -396,13 +405,60 @@ template <bool EXACT, bool COUNTS, bool PEER, int MINB>
 __global__ void __launch_bounds__(32, MINB)
 walk2_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, double* __restrict__ acc_t,
              uint32_t slot_begin, uint32_t slot_end, double theta2, unsigned long long* __restrict__ wcounts,
-             P2P p2p, const uint32_t* __restrict__ flat, int lshift) {
+             P2P p2p, const uint32_t* __restrict__ flat, int lshift, const uint32_t* __restrict__ gorder,
+             uint32_t* __restrict__ gcost) {
   pdl_sync();
   __shared__ W2Smem<EXACT> S;
   if (!EXACT && !COUNTS && flat[3])
-    walk2_body<EXACT, COUNTS, PEER, true>(S, nodes, posm, acc_t, slot_begin, slot_end, theta2, wcounts, p2p, lshift);
+    walk2_body<EXACT, COUNTS, PEER, true>(S, nodes, posm, acc_t, slot_begin, slot_end, theta2, wcounts, p2p, lshift, gorder, gcost);
   else
-    walk2_body<EXACT, COUNTS, PEER, false>(S, nodes, posm, acc_t, slot_begin, slot_end, theta2, wcounts, p2p, lshift);
+    walk2_body<EXACT, COUNTS, PEER, false>(S, nodes, posm, acc_t, slot_begin, slot_end, theta2, wcounts, p2p, lshift, gorder, gcost);
+}
+
+// Heaviest-first launch order for the next walk (one CTA): gorder = the groups sorted by descending gcost, by a
+// counting sort on 1024 cost classes.  Every walk launch takes ~0.2 ms beyond its issue-slot work whatever the grid
+// (profiles/README.md): it ends with whatever its last CTAs happen to be, the groups differ by up to 2x in work (std
+// 18 % of the mean), and the hardware hands CTAs to the SMs in index order.  Dealing the heavy groups first shortens
+// that drain of the machine: measured 2.187 -> 2.107 ms at 31251 CTAs (N = 1M) and 0.370 -> 0.303 ms at the 3907 CTAs
+// of a 1/8 shard (profiles/r01_ab_walk_lpt.txt; tests/devtools/launch_model.py predicted -6 % and -15 %).  The order
+// inside a class is whatever the atomics give: results do not depend on which CTA computes which group.
+__global__ void __launch_bounds__(1024) walk_order_kernel(const uint32_t* __restrict__ gcost, uint32_t* __restrict__ gorder,
+                                                          uint32_t ngroups) {
+  pdl_sync();
+  __shared__ uint32_t cls[1024];
+  __shared__ uint32_t red[32];
+  const uint32_t t = threadIdx.x;
+  uint32_t mx = 1u;
+  for (uint32_t g = t; g < ngroups; g += 1024u) mx = max(mx, gcost[g]);
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((t & 31u) == 0u) red[t >> 5] = mx;
+  cls[t] = 0u;
+  __syncthreads();
+  mx = red[t & 31u];
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const double scale = 1023.0 / (double)mx;
+  // class 0 = heaviest
+  for (uint32_t g = t; g < ngroups; g += 1024u) atomicAdd(&cls[1023u - (uint32_t)((double)gcost[g] * scale)], 1u);
+  __syncthreads();
+  // exclusive scan of the 1024 class counts (one per thread)
+  const uint32_t mine = cls[t];
+  uint32_t incl = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((int)(t & 31u) >= o) incl += v;
+  }
+  __syncthreads();
+  if ((t & 31u) == 31u) red[t >> 5] = incl;
+  __syncthreads();
+  uint32_t before = 0u;
+  for (uint32_t w = 0; w < (t >> 5); ++w) before += red[w];
+  __syncthreads();
+  cls[t] = before + incl - mine;
+  __syncthreads();
+  for (uint32_t g = t; g < ngroups; g += 1024u) {
+    const uint32_t pos = atomicAdd(&cls[1023u - (uint32_t)((double)gcost[g] * scale)], 1u);
+    gorder[pos] = g;
+  }
 }
 
 }  // namespace kdnb
