@@ -185,6 +185,32 @@ def test_build_forced_64_bit_sort_matches():
         assert np.array_equal(out["k32"], out["k64"]) and np.array_equal(out["k32"], out["stubs"])
 
 
+def test_walk_launch_order_does_not_change_results():
+    """The production walk hands out its 32-particle groups heaviest first (previous step's work, walk_order_kernel).
+    Which CTA computes which group must not matter: accelerations of the 2nd and 3rd walk (the ordered ones) and the
+    state after 4 steps are bit-identical with KDNB_WALK_LPT=0 (index order)."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    code = ("import sys, numpy as np, multilanguagekdtree_b200 as kd\n"
+            "p = kd.circular_orbits(30000, seed=8)\n"
+            "s = kd.KDTreeSim(); s.upload(p); acc = []\n"
+            "for k in range(3):\n"
+            "    s.build_tree(); s.calc_accel(); acc.append(s.accel()); s.kick_drift(1e-3)\n"
+            "s.simple_sim(1e-3, 4)\n"
+            "np.savez(sys.argv[1], acc=np.stack(acc), out=s.download())\n")
+    with tempfile.TemporaryDirectory() as d:
+        res = {}
+        for tag, env in (("lpt", {}), ("index", {"KDNB_WALK_LPT": "0"})):
+            f = os.path.join(d, tag + ".npz")
+            subprocess.run([sys.executable, "-c", code, f], check=True, env={**os.environ, **env},
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            res[tag] = np.load(f)
+        assert np.array_equal(bits(res["lpt"]["acc"]), bits(res["index"]["acc"]))
+        assert res["lpt"]["out"].tobytes() == res["index"]["out"].tobytes()
+
+
 def test_build_vs_faithful_reference_order(orc):
     """Against the reference's own summation order (random pivots): everything order-independent is bit-exact,
     m / cm agree to the reference's run-to-run noise."""
