@@ -33,8 +33,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, f) for f in CU]
     deps = srcs + [os.path.join(CSRC, f) for f in ("common.cuh", "ctx.cuh", "walk2.cuh", "walk_legacy.cuh")] + [os.path.join(HERE, "..", "include", "kdnb.h")]
-    if force or not _newer(LIB, deps):
-        cmd = [nvcc, *NVCC_FLAGS, "-shared", "-o", LIB, *srcs, "-ldl"]
+    extra = os.environ.get("KDNB_NVCC_EXTRA", "").split()   # compile-time experiment knobs, e.g. -DKDNB_BOT_CAP=1024
+    if force or extra or not _newer(LIB, deps):
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-shared", "-o", LIB, *srcs, "-ldl"]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -265,7 +265,10 @@ struct __align__(4) BotTab {
 };
 static_assert(sizeof(BotTab) == 12, "BotTab");
 
-constexpr int BOT_THREADS = 512;
+#ifndef KDNB_BOT_THREADS
+#define KDNB_BOT_THREADS 512
+#endif
+constexpr int BOT_THREADS = KDNB_BOT_THREADS;
 constexpr int BOT_IPT = BOT_CAP / BOT_THREADS;  // 4
 constexpr int BOT_WARPS = BOT_THREADS / 32;
 
@@ -494,7 +497,7 @@ build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_
   __syncthreads();
   // {M, sum m*x, sum m*y, sum m*z} of the nodes of this segment live in shared memory (over the id / list buffers,
   // dead from here on); only the segment root's goes to global memory, for build_topup
-  static_assert(sizeof(S.gid) + sizeof(S.lst) >= 1024 * 4 * sizeof(double), "node sums alias gid + lst (heap <= 1024)");
+  static_assert(sizeof(S.gid) + sizeof(S.lst) >= (BOT_CAP / 2) * 4 * sizeof(double), "node sums alias gid + lst (heap <= BOT_CAP / 2 at MAX_PARTS >= 4)");
   double* msl = reinterpret_cast<double*>(smem_raw);
   for (uint32_t h = 1 + tid; h < hend; h += BOT_THREADS) {
     BotTab t = S.tab[h];

@@ -34,7 +34,10 @@ struct __align__(32) PosM {
   double x, y, z, m;
 };
 
-constexpr int BOT_CAP = 2048;  // largest segment handled entirely in shared memory by the bottom build kernel
+#ifndef KDNB_BOT_CAP
+#define KDNB_BOT_CAP 2048  // (compile-time experiment knob: -DKDNB_BOT_CAP=1024 -DKDNB_BOT_THREADS=256, see build.py)
+#endif
+constexpr int BOT_CAP = KDNB_BOT_CAP;  // largest segment handled entirely in shared memory by the bottom build kernel
 constexpr int MAX_LEVELS = 40;
 
 // per-size node-count tables are closed-form; see subtree_nodes() in build.cu

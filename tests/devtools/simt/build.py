@@ -16,12 +16,13 @@ def build(verbose: bool = False) -> str:
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     objs = []
     flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-fopenmp", "-ffp-contract=off", "-mfma", "-Wno-unknown-pragmas",
-             "-Wno-attributes", "-I", HERE, "-I", CSRC]
+             "-Wno-attributes", "-I", HERE, "-I", CSRC, *os.environ.get("KDNB_NVCC_EXTRA", "").split()]
+    force = bool(os.environ.get("KDNB_NVCC_EXTRA"))
     for f in CU + ["simt_runtime.cpp"]:
         src = os.path.join(CSRC, f) if f.endswith(".cu") else os.path.join(HERE, f)
         obj = os.path.join(HERE, "_build", f.replace(".cu", ".o").replace(".cpp", ".o"))
         deps = [src, os.path.join(HERE, "cuda_runtime.h")] + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".hpp"))]
-        if os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps):
+        if not force and os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps):
             objs.append(obj)
             continue
         cmd = ["g++", *flags, "-x", "c++", "-c", src, "-o", obj]
