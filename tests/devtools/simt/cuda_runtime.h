@@ -306,8 +306,23 @@ static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEve
   *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
   return cudaSuccess;
 }
-static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+// "peer" contexts of the multi-rank model are threads of this process (multirank.py), so a handle is the pointer itself
+// (SIMT_IPC=0: not supported, as on a machine without peer access — the library then exchanges through NCCL)
+static inline bool simt_ipc_on() {
+  static const bool on = [] { const char* e = getenv("SIMT_IPC"); return !e || atoi(e) != 0; }();
+  return on;
+}
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+  if (!simt_ipc_on()) return cudaErrorNotSupported;
+  memset(h, 0, sizeof *h);
+  memcpy(h->reserved, &p, sizeof p);
+  return cudaSuccess;
+}
+static inline cudaError_t cudaIpcOpenMemHandle(void** out, cudaIpcMemHandle_t h, unsigned) {
+  if (!simt_ipc_on()) return cudaErrorNotSupported;
+  memcpy(out, h.reserved, sizeof *out);
+  return cudaSuccess;
+}
 static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 template <typename F>
 static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }

@@ -25,3 +25,19 @@ def test_kernel_sources_under_the_simt_model_match_the_oracle():
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("ipc", ["1", "0"])
+def test_two_ranks_under_the_simt_model_are_bit_identical_to_one(ipc):
+    """World size 2 of the multi-GPU path on the CPU: the ranks are threads of one process, every rank's kernels run
+    under the SIMT model, NCCL is tests/devtools/simt/fake_nccl.cpp and cudaIpc handles are plain pointers
+    (tests/devtools/simt/multirank.py).  ipc=1: accelerations exchanged by peer stores from inside the walk kernel +
+    flag handshake + wait kernel; ipc=0: peer mapping "unavailable", the library falls back on ncclAllGather.  Either way
+    replicated build + sharded walk + exchange + kick/drift, and the sharded host-buffer calls, must give every rank
+    the bits of a single-rank run."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "devtools", "simt", "multirank.py"), "2", "3000", "3"],
+                       capture_output=True, text=True, cwd=ROOT, env={**os.environ, "SIMT_IPC": ipc})
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0 and "multirank ok: world=2" in r.stdout, tail
+    assert ("peer stores" in r.stdout) == (ipc == "1"), tail
