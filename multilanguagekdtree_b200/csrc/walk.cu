@@ -38,7 +38,7 @@ template <int PPL, int MINB, int WALK_THREADS = 64, int DW = 4>
 static void launch_walk(Ctx* c, uint32_t begin, uint32_t end) {
   constexpr int WALK_WARPS = WALK_THREADS / 32;
   const uint32_t groups = (end - begin + 32 * PPL - 1) / (32 * PPL);
-  const uint32_t grid = (groups + WALK_WARPS - 1) / WALK_WARPS;
+  const uint32_t grid = std::max<uint32_t>((groups + WALK_WARPS - 1) / WALK_WARPS, 1u);
   const bool counts = (c->flags & KDNB_FLAG_WALK_COUNTS) != 0;
   const bool exact = (c->flags & KDNB_FLAG_EXACT_MATH) != 0;
   P2P pp = c->p2p;
@@ -59,7 +59,7 @@ static void launch_walk(Ctx* c, uint32_t begin, uint32_t end) {
 }
 
 static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
-  const uint32_t grid = (end - begin + 31) / 32;
+  const uint32_t grid = std::max<uint32_t>((end - begin + 31) / 32, 1u);
   const bool counts = (c->flags & KDNB_FLAG_WALK_COUNTS) != 0;
   const bool exact = (c->flags & KDNB_FLAG_EXACT_MATH) != 0;
   P2P pp = c->p2p;
@@ -118,7 +118,10 @@ int walk(Ctx* c) {
     begin = (uint32_t)std::min<uint64_t>(c->n, (uint64_t)c->rank_id * c->shard_slots);
     end = (uint32_t)std::min<uint64_t>(c->n, (uint64_t)(c->rank_id + 1) * c->shard_slots);
   }
-  if (end > begin) {
+  // (peer mode: a rank whose shard is empty — fewer particles than 64 x (world - 1) — still launches one CTA, which has
+  // nothing to walk but raises this rank's flag on every peer; without it all ranks would wait for the flag until the
+  // wait kernel's timeout, every step)
+  if (end > begin || (c->world > 1 && c->p2p_on)) {
     static const int cfg = [] {
       const char* s = getenv("KDNB_WALK_CFG");  // profiling knob: 0 = walk2 (default), anything else = the previous kernel
       return s ? atoi(s) : 0;

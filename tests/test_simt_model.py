@@ -41,3 +41,13 @@ def test_two_ranks_under_the_simt_model_are_bit_identical_to_one(ipc):
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0 and "multirank ok: world=2" in r.stdout, tail
     assert ("peer stores" in r.stdout) == (ipc == "1"), tail
+
+
+@pytest.mark.timeout(600)
+def test_ranks_with_empty_shards_under_the_simt_model():
+    """Fewer particles than 64 x (world - 1): some ranks have nothing to walk.  In peer mode they must still raise their
+    flag (one idle CTA) or every rank waits for it until the wait kernel's timeout, every step — found by this model."""
+    for world, n in (("2", "33"), ("4", "100")):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "devtools", "simt", "multirank.py"), world, n, "2"],
+                           capture_output=True, text=True, cwd=ROOT, timeout=300)
+        assert r.returncode == 0 and f"multirank ok: world={world}" in r.stdout, (r.stdout + r.stderr)[-2000:]
