@@ -293,7 +293,10 @@ static inline uint32_t bot_heap(uint32_t mp) {
 }
 static inline size_t bot_smem_bytes(uint32_t mp) { return sizeof(BotSmem) + (bot_heap(mp) - 1) * sizeof(BotTab); }
 
-__global__ void __launch_bounds__(BOT_THREADS, 4)
+#ifndef KDNB_BOT_MINB
+#define KDNB_BOT_MINB 4
+#endif
+__global__ void __launch_bounds__(BOT_THREADS, KDNB_BOT_MINB)
 build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_t mp, int layout,
              const uint4* __restrict__ tseg, uint32_t* __restrict__ inv, WNode* __restrict__ nodes,
              double4* __restrict__ ms, uint32_t* __restrict__ perm, uint32_t* __restrict__ rank,
