@@ -20,6 +20,23 @@ lib = simt_build.build()
 from multilanguagekdtree_b200 import _lib  # noqa: E402
 
 _lib.LIB_PATH = lib
+
+# Tests that start a fresh process (a python child importing the package, the kdtree-sim binary) are re-pointed too, from
+# the TEST side only: a sitecustomize on the children's PYTHONPATH sets the loader path, and a directory holding a
+# `libkdnb.so` link to the emulated library goes first on LD_LIBRARY_PATH (kdtree-sim finds its library by RUNPATH,
+# which is searched after it).  Nothing under multilanguagekdtree_b200/ knows about either.
+_site = os.path.join(HERE, "_build", "site")
+_libdir = os.path.join(HERE, "_build", "libdir")
+os.makedirs(_site, exist_ok=True)
+os.makedirs(_libdir, exist_ok=True)
+with open(os.path.join(_site, "sitecustomize.py"), "w") as f:
+    f.write("import sys\nsys.path.insert(0, %r)\nfrom multilanguagekdtree_b200 import _lib\n_lib.LIB_PATH = %r\n" % (ROOT, lib))
+_link = os.path.join(_libdir, "libkdnb.so")
+if os.path.islink(_link) or os.path.exists(_link):
+    os.remove(_link)
+os.symlink(lib, _link)
+os.environ["PYTHONPATH"] = _site + os.pathsep + os.environ.get("PYTHONPATH", "")
+os.environ["LD_LIBRARY_PATH"] = _libdir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", "")
 import pytest  # noqa: E402
 
 sys.exit(pytest.main(["-m", "gpu", os.path.join(ROOT, "tests", "test_gpu_parity.py"), *sys.argv[1:]]))
