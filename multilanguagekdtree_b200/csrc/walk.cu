@@ -67,11 +67,18 @@ static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
   int lshift = 0;  // lanes per leaf in the leaf rounds: the smallest power of two >= MAX_PARTS
   while ((1u << lshift) < c->mp) ++lshift;
   // Heaviest-first launch order from the work the groups reported in the previous walk of the same particle set and
-  // shard (the tree order moves little from step to step).  Production kernel only; KDNB_WALK_LPT=0 disables.
-  static const bool lpt = [] {
+  // shard (the tree order moves little from step to step).  Production kernel only, and only while the node records
+  // and tree-ordered particles (~66 B per particle) fit the 126 MB L2: the index order is also the spatial order, so
+  // the ~3500 groups in flight share their near field; with the cost order they are scattered over the whole domain,
+  // which costs nothing when the tree is L2-resident (measured at N = 125k and 1M) but has not been measured where it
+  // is not (N >= 10M streams the tree from HBM) — there the launch stays in index order.
+  // KDNB_WALK_LPT=0 disables, =1 forces it at every size.
+  static const int lpt_mode = [] {
     const char* s = getenv("KDNB_WALK_LPT");
-    return s ? atoi(s) != 0 : true;
+    return s ? (atoi(s) != 0 ? 1 : 0) : -1;
   }();
+  constexpr uint64_t LPT_MAX_N = 1ull << 21;
+  const bool lpt = lpt_mode == 1 || (lpt_mode < 0 && c->n <= LPT_MAX_N);
   const bool production = !exact && !counts;
   const uint32_t* gorder = nullptr;
   uint32_t* gcost = nullptr;
