@@ -113,7 +113,8 @@ int kdnb_simple_sim(kdnb_ctx* ctx, double dt, int64_t steps); /* on the uploaded
 int kdnb_simple_sim_host(const kdnb_config* cfg, kdnb_particle* bodies, uint64_t count, double dt, int64_t steps);
 /* the same on an existing context (buffers are reused across calls): upload + `steps` steps + download */
 int kdnb_simple_sim_bodies(kdnb_ctx* ctx, kdnb_particle* bodies, uint64_t count, double dt, int64_t steps);
-int kdnb_synchronize(kdnb_ctx* ctx);
+int kdnb_synchronize(kdnb_ctx* ctx); /* also reports what only the device saw: a build look-back or (multi-GPU) a peer that
+                                       never published its accelerations within ~15 s; so do the particle downloads */
 
 /* ---- results of the stages (parity hooks) */
 int kdnb_download_accel(kdnb_ctx* ctx, double* acc /* count*3, original particle order */);

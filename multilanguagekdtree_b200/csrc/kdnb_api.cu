@@ -315,6 +315,17 @@ static int exchange(Ctx* c) {
   return 0;
 }
 
+// multi-GPU, peer mode: the wait kernel gives up after ~15 s when a peer never publishes its accelerations (walk.cu)
+// and records it; the step then ran on incomplete accelerations, so the caller must hear about it
+static int check_peer_timeout(Ctx* c) {
+  if (c->world <= 1 || !c->p2p_on || !c->p2p_state) return 0;
+  uint32_t err = 0;
+  KDNB_CUDA_TRY(c, cudaMemcpyAsync(&err, c->p2p_state + 2, sizeof(err), cudaMemcpyDeviceToHost, c->stream));
+  KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (err) return c->fail(KDNB_E_CUDA, "multi-GPU exchange: a peer did not publish its accelerations in time (results are incomplete)");
+  return 0;
+}
+
 static int one_step(Ctx* c, double dt) {
   const bool prof = (c->flags & KDNB_FLAG_PROFILE) && c->ev_steps < 4096;
   cudaEvent_t* e = nullptr;
@@ -455,7 +466,7 @@ int kdnb_download_particles(kdnb_ctx* ctx, kdnb_particle* out, uint64_t capacity
   if (int rc = soa_to_aos(c)) return rc;
   KDNB_CUDA_TRY(c, cudaMemcpyAsync(out, c->aos, c->n * sizeof(kdnb_particle), cudaMemcpyDeviceToHost, c->stream));
   KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  return 0;
+  return check_peer_timeout(c);
 }
 
 uint64_t kdnb_particle_count(const kdnb_ctx* ctx) { return ctx ? ctx->c.n : 0; }
@@ -588,7 +599,7 @@ int kdnb_download_particles_sharded(kdnb_ctx* ctx, kdnb_particle* shard_out) {
   if (int rc = soa_to_aos(c)) return rc;  // every replica holds the full, bit-identical state
   if (cnt) KDNB_CUDA_TRY(c, cudaMemcpyAsync(shard_out, c->aos + first, cnt * sizeof(kdnb_particle), cudaMemcpyDeviceToHost, c->stream));
   KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  return 0;
+  return check_peer_timeout(c);
 }
 
 int kdnb_simple_sim_bodies_sharded(kdnb_ctx* ctx, kdnb_particle* shard, uint64_t total, double dt, int64_t steps) {
@@ -615,6 +626,7 @@ int kdnb_simple_sim_host(const kdnb_config* cfg, kdnb_particle* bodies, uint64_t
 int kdnb_synchronize(kdnb_ctx* ctx) {
   CTX_OR_FAIL(ctx);
   KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (int rc = check_peer_timeout(c)) return rc;
   if (c->lvl_ctl) {  // a look-back of the level partitions that gave up instead of spinning for ever (build.cu)
     uint32_t err = 0;
     KDNB_CUDA_TRY(c, cudaMemcpyAsync(&err, c->lvl_ctl + 65, sizeof(err), cudaMemcpyDeviceToHost, c->stream));
