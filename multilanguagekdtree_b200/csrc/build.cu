@@ -137,23 +137,6 @@ __device__ __forceinline__ SegStats seg_stats(Pos3c pos, Lists L, int level, uin
 // launches unreadable, so the array is never cleared.  (History: a count + scatter kernel pair per level; then one
 // look-back kernel with a CTA per (list, chunk) that copied the split-dimension list — two thirds of those CTAs only
 // learnt that they had nothing to partition.)
-__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
-#ifdef KDNB_SIMT
-  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
-#else
-  unsigned long long v;
-  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
-  return v;
-#endif
-}
-__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
-#ifdef KDNB_SIMT
-  __atomic_store_n(p, v, __ATOMIC_RELEASE);
-#else
-  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-#endif
-}
-
 template <int MINB>
 __global__ void __launch_bounds__(LVL_THREADS, MINB)
 level_partition(Pos3c pos, Lists L, int level, uint32_t cps, uint32_t mp, int layout, uint4* __restrict__ tseg,
@@ -302,11 +285,7 @@ build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_
              double4* __restrict__ ms, uint32_t* __restrict__ perm, uint32_t* __restrict__ rank,
              PosM* __restrict__ posm, const uint32_t* __restrict__ flat, uint32_t heap) {
   pdl_sync();
-#ifdef KDNB_SIMT
-  unsigned char* const smem_raw = simt::dyn_smem();
-#else
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-#endif
+  KDNB_DYN_SMEM(smem_raw);
   BotSmem& S = *reinterpret_cast<BotSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t lt = (1u << lane) - 1u;

@@ -62,7 +62,8 @@ struct Ctx {
   uint32_t* hist = nullptr;                // [3][256][ntiles]
   uint32_t* digit_tot = nullptr;           // [3][256]
   uint32_t* flat = nullptr;                // [3] 1 = all coordinates of that dimension equal (lives behind digit_tot); [3] planar walk
-  uint64_t* sort_state = nullptr;          // [16] key range, 32-bit key scaling, need64 flag (sort.cu)
+  uint64_t* sort_state = nullptr;          // [SS_WORDS] 32-bit key scaling, need64 flag, running position extents (common.cuh)
+  bool extent_fresh = false;               // the extent records describe the current positions and were not consumed yet
   uint32_t* rk = nullptr;                  // [3][n] rank of every particle in the initial sorted list of each dimension
   uint4* tseg = nullptr;                   // level table, level l at offset 2^l - 1: {first slot, length, node, buffer bits}
   uint32_t* inv = nullptr;                 // [n] id -> local slot inside a bottom segment
@@ -109,7 +110,8 @@ struct Ctx {
 
   // measurement
   uint64_t launches = 0;
-  std::vector<cudaEvent_t> ev;  // 5 events per profiled step
+  cudaEvent_t pev[5] = {};      // KDNB_FLAG_PROFILE: stage boundaries of the current step (event-record nodes in the step graph)
+  double stage_acc[4] = {0, 0, 0, 0};  // build / walk / exchange / kick ms summed since the last reset
   uint64_t ev_steps = 0;
   cudaEvent_t sw_begin = nullptr, sw_end = nullptr;
   void* l2_scratch = nullptr;

@@ -84,6 +84,7 @@ static int dev_alloc(Ctx* c, T** p, uint64_t count) {
 }
 
 static void close_peers(Ctx* c);
+static void peer_barrier(Ctx* c);
 
 static void free_all(Ctx* c) {
   auto fr = [](auto*& p) {
@@ -115,7 +116,12 @@ static void free_all(Ctx* c) {
   fr(c->perm);
   fr(c->rank);
   c->posm = nullptr;  // lives inside the nodes allocation
+  // acc_t and p2p_state were exported with cudaIpcGetMemHandle: every rank closes its mappings of the peers' buffers
+  // and all ranks meet before anyone frees (freeing exported memory an importer still maps is undefined behaviour).
+  // free_all runs from a growing plan() and from kdnb_destroy, both collective calls when world > 1.
+  const bool exported = c->p2p_on;
   close_peers(c);
+  if (exported) peer_barrier(c);
   fr(c->acc_t);
   fr(c->p2p_state);
   fr(c->wcounts);
@@ -135,13 +141,27 @@ static void close_peers(Ctx* c) {
   c->p2p_ready = false;
 }
 
+// all ranks of the communicator meet here (1-byte all-gather + stream synchronisation); errors are ignored — this is
+// only ever a courtesy to the peers before memory they may still map is released
+static void peer_barrier(Ctx* c) {
+  if (c->world <= 1 || !c->nccl_comm || !g_nccl.all_gather) return;
+  unsigned char* dev = nullptr;
+  if (cudaMalloc(&dev, (size_t)c->world) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  if (g_nccl.all_gather(dev + c->rank_id, dev, 1, NCCL_UINT8, c->nccl_comm, c->stream) == 0) cudaStreamSynchronize(c->stream);
+  cudaGetLastError();
+  cudaFree(dev);
+}
+
 static int setup_peers(Ctx* c) {
   close_peers(c);
   c->p2p_ready = true;  // attempted for this allocation (success or not)
   static const bool disabled = getenv("KDNB_NO_P2P") != nullptr;
   const int W = c->world;
-  KDNB_CUDA_TRY(c, cudaMemsetAsync(c->p2p_state, 0, (4 + P2P_MAX) * sizeof(uint32_t), c->stream));
-  // every rank must take the same decision: exchange {ok, handle(acc), handle(state)} records
+  // every rank must take the same decision and must reach both all-gathers whatever fails locally (a rank that
+  // returned early would leave the others blocked in the collective): local failures vote ok = 0
   struct Rec {
     int ok;
     int pad[15];
@@ -151,21 +171,29 @@ static int setup_peers(Ctx* c) {
   Rec mine;
   memset(&mine, 0, sizeof mine);
   mine.ok = (!disabled && W <= P2P_MAX) ? 1 : 0;
+  if (cudaMemsetAsync(c->p2p_state, 0, (4 + P2P_MAX) * sizeof(uint32_t), c->stream) != cudaSuccess) mine.ok = 0;
   if (mine.ok && cudaIpcGetMemHandle(&mine.acc, c->acc_t) != cudaSuccess) mine.ok = 0;
   if (mine.ok && cudaIpcGetMemHandle(&mine.st, c->p2p_state) != cudaSuccess) mine.ok = 0;
   cudaGetLastError();
   Rec* dev = nullptr;
-  KDNB_CUDA_TRY(c, cudaMalloc(&dev, sizeof(Rec) * W));
-  KDNB_CUDA_TRY(c, cudaMemcpyAsync(dev + c->rank_id, &mine, sizeof(Rec), cudaMemcpyHostToDevice, c->stream));
-  int r = g_nccl.all_gather(dev + c->rank_id, dev, sizeof(Rec), NCCL_UINT8, c->nccl_comm, c->stream);
+  int* dev2 = nullptr;
+  std::string local_err;
+  if (cudaMalloc(&dev, sizeof(Rec) * W) != cudaSuccess || cudaMalloc(&dev2, sizeof(int) * W) != cudaSuccess) {
+    // without scratch this rank cannot even vote: the communicator is unusable for the set-up
+    cudaGetLastError();
+    if (dev) cudaFree(dev);
+    return c->fail(KDNB_E_NOMEM, "peer set-up: cudaMalloc of the exchange scratch failed");
+  }
   Rec all[KDNB_MAX_WORLD];  // W <= KDNB_MAX_WORLD (kdnb_comm_init)
-  cudaError_t e = cudaMemcpyAsync(all, dev, sizeof(Rec) * W, cudaMemcpyDeviceToHost, c->stream);
+  memset(all, 0, sizeof all);
+  cudaError_t e = cudaMemcpyAsync(dev + c->rank_id, &mine, sizeof(Rec), cudaMemcpyHostToDevice, c->stream);
+  int r = g_nccl.all_gather(dev + c->rank_id, dev, sizeof(Rec), NCCL_UINT8, c->nccl_comm, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(all, dev, sizeof(Rec) * W, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  cudaFree(dev);
-  if (r != 0) return c->fail(KDNB_E_NCCL, "ncclAllGather(ipc handles) failed");
-  if (e != cudaSuccess) return c->fail(KDNB_E_CUDA, std::string("ipc handle exchange: ") + cudaGetErrorString(e));
-  bool ok = true;
-  for (int k = 0; k < W; ++k) ok = ok && all[k].ok;
+  if (r != 0) local_err = "ncclAllGather(ipc handles) failed";
+  else if (e != cudaSuccess) local_err = std::string("ipc handle exchange: ") + cudaGetErrorString(e);
+  bool ok = local_err.empty();
+  for (int k = 0; ok && k < W; ++k) ok = ok && all[k].ok;
   P2P pp;
   memset(&pp, 0, sizeof pp);
   for (int k = 0; ok && k < W; ++k) {
@@ -188,21 +216,22 @@ static int setup_peers(Ctx* c) {
     pp.flags[k] = reinterpret_cast<uint32_t*>(ps) + 4;
   }
   // second round: peer mode only if EVERY rank mapped every peer (otherwise all fall back to ncclAllGather)
-  int* dev2 = nullptr;
-  KDNB_CUDA_TRY(c, cudaMalloc(&dev2, sizeof(int) * W));
   int okv = ok ? 1 : 0;
-  KDNB_CUDA_TRY(c, cudaMemcpyAsync(dev2 + c->rank_id, &okv, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  r = g_nccl.all_gather(dev2 + c->rank_id, dev2, sizeof(int), NCCL_UINT8, c->nccl_comm, c->stream);
   int oks[KDNB_MAX_WORLD];
-  e = cudaMemcpyAsync(oks, dev2, sizeof(int) * W, cudaMemcpyDeviceToHost, c->stream);
+  memset(oks, 0, sizeof oks);
+  e = cudaMemcpyAsync(dev2 + c->rank_id, &okv, sizeof(int), cudaMemcpyHostToDevice, c->stream);
+  r = g_nccl.all_gather(dev2 + c->rank_id, dev2, sizeof(int), NCCL_UINT8, c->nccl_comm, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(oks, dev2, sizeof(int) * W, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(dev);
   cudaFree(dev2);
-  if (r != 0 || e != cudaSuccess) return c->fail(KDNB_E_NCCL, "peer set-up vote failed");
+  if ((r != 0 || e != cudaSuccess) && local_err.empty()) local_err = "peer set-up vote failed";
   for (int k = 0; k < W; ++k) ok = ok && oks[k];
-  if (!ok) {
+  if (!ok || !local_err.empty()) {
     const bool keep = c->p2p_ready;
     close_peers(c);
     c->p2p_ready = keep;
+    if (!local_err.empty()) return c->fail(KDNB_E_NCCL, local_err);
     return 0;  // NCCL exchange
   }
   pp.epoch = c->p2p_state;
@@ -262,15 +291,18 @@ static int plan(Ctx* c, uint64_t n) {
     if (!rc) rc = dev_alloc(c, &c->hist, 3ull * 256 * c->ntiles);
     if (!rc) rc = dev_alloc(c, &c->digit_tot, 3 * 256 + 4);
     if (!rc) c->flat = c->digit_tot + 3 * 256;
-    if (!rc) rc = dev_alloc(c, &c->sort_state, 16);
+    if (!rc) rc = dev_alloc(c, &c->sort_state, SS_WORDS);
     if (!rc) rc = dev_alloc(c, &c->rk, 3 * n);
     if (!rc) rc = dev_alloc(c, &c->pm, n);
     if (!rc) rc = dev_alloc(c, &c->inv, n);
     if (!rc) rc = dev_alloc(c, &c->tseg, table);
     if (!rc) rc = dev_alloc(c, &c->lvl_status, chunks);
     if (!rc) rc = dev_alloc(c, &c->lvl_ctl, 72);
-    if (!rc) KDNB_CUDA_TRY(c, cudaMemsetAsync(c->lvl_status, 0, chunks * sizeof(uint64_t), c->stream));
-    if (!rc) KDNB_CUDA_TRY(c, cudaMemsetAsync(c->lvl_ctl, 0, 72 * sizeof(uint32_t), c->stream));
+    auto cuda_rc = [&](cudaError_t e, const char* what) {
+      return e == cudaSuccess ? 0 : c->fail(KDNB_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    };
+    if (!rc) rc = cuda_rc(cudaMemsetAsync(c->lvl_status, 0, chunks * sizeof(uint64_t), c->stream), "cudaMemsetAsync(lvl_status)");
+    if (!rc) rc = cuda_rc(cudaMemsetAsync(c->lvl_ctl, 0, 72 * sizeof(uint32_t), c->stream), "cudaMemsetAsync(lvl_ctl)");
     if (!rc) rc = dev_alloc(c, &c->nodes, c->n_nodes + (n + 1) / 2 + 1);  // node records, then the tree-ordered particles (one pool: walk.cu)
     if (!rc) rc = dev_alloc(c, &c->ms, c->n_nodes);
     if (!rc) rc = dev_alloc(c, &c->perm, n);
@@ -283,9 +315,11 @@ static int plan(Ctx* c, uint64_t n) {
     if (!rc) rc = dev_alloc(c, &c->gcost, n / 32 + 2);
     if (!rc) rc = dev_alloc(c, &c->gorder, n / 32 + 2);
     if (rc) {
+      const std::string why = c->err;
       free_all(c);
       c->cap = c->node_cap = c->table_cap = c->chunk_cap = 0;
-      c->n = 0;
+      c->n = c->planned_n = 0;
+      c->err = why;
       return rc;
     }
   }
@@ -326,31 +360,39 @@ static int check_peer_timeout(Ctx* c) {
   return 0;
 }
 
-static int one_step(Ctx* c, double dt) {
-  const bool prof = (c->flags & KDNB_FLAG_PROFILE) && c->ev_steps < 4096;
-  cudaEvent_t* e = nullptr;
-  if (prof) {
-    if (c->ev.size() < (c->ev_steps + 1) * 5) {
-      for (int k = 0; k < 5; ++k) {
-        cudaEvent_t x;
-        KDNB_CUDA_TRY(c, cudaEventCreate(&x));
-        c->ev.push_back(x);
-      }
-    }
-    e = &c->ev[c->ev_steps * 5];
-    cudaEventRecord(e[0], c->stream);
+// One step.  KDNB_FLAG_PROFILE: the four stage boundaries are recorded as events — external event-record nodes when the
+// step is being captured into the step graph, so that the stage times come from the SAME execution mode (graph replay)
+// as the timed region of bench.py; stage_collect() reads them after every profiled step.
+static int one_step(Ctx* c, double dt, bool capturing = false) {
+  const bool prof = (c->flags & KDNB_FLAG_PROFILE) != 0;
+  if (prof && !c->pev[0]) {
+    for (int k = 0; k < 5; ++k) KDNB_CUDA_TRY(c, cudaEventCreate(&c->pev[k]));
   }
+  auto mark = [&](int k) {
+    if (prof) cudaEventRecordWithFlags(c->pev[k], c->stream, capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+  };
+  mark(0);
   if (int rc = build_tree(c)) return rc;  // indices reset + build_tree_par4 (:641-643)
-  if (prof) cudaEventRecord(e[1], c->stream);
+  mark(1);
   if (int rc = walk(c)) return rc;        // calc_accel for every particle (:647)
-  if (prof) cudaEventRecord(e[2], c->stream);
+  mark(2);
   if (int rc = exchange(c)) return rc;
-  if (prof) cudaEventRecord(e[3], c->stream);
+  mark(3);
   if (int rc = kick_drift(c, dt)) return rc;  // (:649-662)
-  if (prof) {
-    cudaEventRecord(e[4], c->stream);
-    c->ev_steps++;
+  mark(4);
+  return 0;
+}
+
+// profiled contexts: wait for the step just enqueued and add its stage times to the sums
+static int stage_collect(Ctx* c) {
+  if (!(c->flags & KDNB_FLAG_PROFILE) || !c->pev[0]) return 0;
+  KDNB_CUDA_TRY(c, cudaEventSynchronize(c->pev[4]));
+  for (int k = 0; k < 4; ++k) {
+    float t = 0.f;
+    KDNB_CUDA_TRY(c, cudaEventElapsedTime(&t, c->pev[k], c->pev[k + 1]));
+    c->stage_acc[k] += t;
   }
+  c->ev_steps++;
   return 0;
 }
 
@@ -417,10 +459,12 @@ void kdnb_destroy(kdnb_ctx* ctx) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   drop_graph_if_any(c);
+  free_all(c);  // (world > 1 in peer mode: meets the other ranks before the exported buffers go — destroy is collective)
   if (c->nccl_comm && g_nccl.comm_destroy) g_nccl.comm_destroy(c->nccl_comm);
-  free_all(c);
+  c->nccl_comm = nullptr;
   if (c->l2_scratch) cudaFree(c->l2_scratch);
-  for (cudaEvent_t x : c->ev) cudaEventDestroy(x);
+  for (cudaEvent_t x : c->pev)
+    if (x) cudaEventDestroy(x);
   if (c->sw_begin) cudaEventDestroy(c->sw_begin);
   if (c->sw_end) cudaEventDestroy(c->sw_end);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -506,15 +550,17 @@ int kdnb_kick_drift(kdnb_ctx* ctx, double dt) {
 int kdnb_simple_sim(kdnb_ctx* ctx, double dt, int64_t steps) {
   CTX_OR_FAIL(ctx);
   NEED_PARTICLES(c);
-  if (c->empty) return 0;
+  if (c->empty || steps <= 0) return 0;  // `for _ in 0..steps` (array_kd_tree.rs:632) runs nothing
   int64_t s = 0;
   // Launch-bound regime (N <= ~1M: ~35 kernels of 5-35 us per step): replay the step as one CUDA graph.  A graph is
   // captured by a call of >= 3 steps, or by the third consecutive call with the same (n, dt) — a caller stepping one
   // step per call, like the reference's own loop around its closure; once it exists every step of a matching call
   // replays it.  The step before a capture always runs as plain launches (lazy one-time setup: function attributes,
-  // NCCL connections).
+  // NCCL connections).  Profiled contexts replay the same graph (with event-record nodes at the stage boundaries) and
+  // wait for every step to read them.
   static const bool no_graph = getenv("KDNB_NO_GRAPH") != nullptr;
-  const bool can_graph = !(c->flags & KDNB_FLAG_PROFILE) && !no_graph;
+  const bool prof = (c->flags & KDNB_FLAG_PROFILE) != 0;
+  const bool can_graph = !no_graph;
   const bool have = c->step_graph && c->graph_n == c->n && c->graph_dt == dt && c->graph_world == c->world;
   if (c->seen_n == c->n && c->seen_dt == dt) {
     c->seen_calls++;
@@ -527,11 +573,12 @@ int kdnb_simple_sim(kdnb_ctx* ctx, double dt, int64_t steps) {
   if (use_graph) {
     if (!have) {
       if (int rc = one_step(c, dt)) return rc;
+      if (int rc = stage_collect(c)) return rc;
       s = 1;
       drop_graph_if_any(c);
       const uint64_t l0 = c->launches;
       KDNB_CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-      const int rc = one_step(c, dt);
+      const int rc = one_step(c, dt, true);
       cudaGraph_t g = nullptr;
       cudaError_t e = cudaStreamEndCapture(c->stream, &g);
       c->graph_launches = c->launches - l0;
@@ -554,11 +601,16 @@ int kdnb_simple_sim(kdnb_ctx* ctx, double dt, int64_t steps) {
     for (; s < steps; ++s) {
       KDNB_CUDA_TRY(c, cudaGraphLaunch(c->step_graph, c->stream));
       c->launches += c->graph_launches;
+      if (prof)
+        if (int rc = stage_collect(c)) return rc;
     }
     return 0;
   }
-  for (; s < steps; ++s)
+  for (; s < steps; ++s) {
     if (int rc = one_step(c, dt)) return rc;
+    if (prof)
+      if (int rc = stage_collect(c)) return rc;
+  }
   return 0;
 }
 
@@ -762,8 +814,11 @@ int kdnb_comm_init(kdnb_ctx* ctx, const void* id_bytes, int rank, int world_size
   memcpy(&id, id_bytes, sizeof id);
   void* comm = nullptr;
   int r = g_nccl.comm_init_rank(&comm, world_size, id, rank);
-  if (r != 0)
+  if (r != 0) {
+    c->rank_id = 0;  // (a failed re-join leaves a working single-rank context, not world > 1 without a communicator)
+    c->world = 1;
     return c->fail(KDNB_E_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.get_error_string ? g_nccl.get_error_string(r) : "error"));
+  }
   c->nccl_comm = comm;
   c->rank_id = rank;
   c->world = world_size;
@@ -780,18 +835,10 @@ int kdnb_stage_ms(kdnb_ctx* ctx, double ms_out[KDNB_STAGE_COUNT], uint64_t* step
   if (!(c->flags & KDNB_FLAG_PROFILE)) return c->fail(KDNB_E_INVALID, "context was created without KDNB_FLAG_PROFILE");
   KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   for (int k = 0; k < KDNB_STAGE_COUNT; ++k) ms_out[k] = 0.0;
-  for (uint64_t s = 0; s < c->ev_steps; ++s) {
-    cudaEvent_t* e = &c->ev[s * 5];
-    float t;
-    cudaEventElapsedTime(&t, e[0], e[1]);
-    ms_out[KDNB_STAGE_BUILD] += t;
-    cudaEventElapsedTime(&t, e[1], e[2]);
-    ms_out[KDNB_STAGE_WALK] += t;
-    cudaEventElapsedTime(&t, e[2], e[3]);
-    ms_out[KDNB_STAGE_EXCHANGE] += t;
-    cudaEventElapsedTime(&t, e[3], e[4]);
-    ms_out[KDNB_STAGE_KICK] += t;
-  }
+  ms_out[KDNB_STAGE_BUILD] = c->stage_acc[0];
+  ms_out[KDNB_STAGE_WALK] = c->stage_acc[1];
+  ms_out[KDNB_STAGE_EXCHANGE] = c->stage_acc[2];
+  ms_out[KDNB_STAGE_KICK] = c->stage_acc[3];
   if (steps_out) *steps_out = c->ev_steps;
   return 0;
 }
@@ -800,6 +847,7 @@ int kdnb_stage_reset(kdnb_ctx* ctx) {
   CTX_OR_FAIL(ctx);
   KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   c->ev_steps = 0;
+  for (double& x : c->stage_acc) x = 0.0;
   return 0;
 }
 

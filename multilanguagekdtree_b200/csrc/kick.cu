@@ -2,6 +2,8 @@
 // AoS <-> SoA conversions at the C-ABI boundary (Particle, array_particle.rs:3-8).
 // Bandwidth-bound elementwise kernels; arithmetic is unfused (__dmul_rn / __dadd_rn) so that results are
 // bit-identical to the reference's `v += dt*a; p += dt*v` given the same accelerations.
+#include <algorithm>
+
 #include "ctx.cuh"
 
 namespace kdnb {
@@ -28,77 +30,96 @@ static AccSel acc_sel(const Ctx* c) {
   return a;
 }
 
-// thread i = particle i (original order); its acceleration lives at tree slot rank[i]
+// thread i = particle i (original order); its acceleration lives at tree slot rank[i].  The same thread zeroes that
+// acceleration (a[k] = 0, :659-661) and folds the new position into the extents the next build's sort scales its keys
+// to (accumulate_extent, common.cuh): the step has no separate pass over the positions.
 __global__ void __launch_bounds__(256) kick_drift_kernel(uint32_t n, double dt, V3 pos, V3 vel,
                                                          const uint32_t* __restrict__ rank, AccSel sel,
-                                                         PosM* __restrict__ pm) {
+                                                         PosM* __restrict__ pm, uint64_t* __restrict__ ss) {
   pdl_sync();
+  __shared__ uint64_t sm[8][8];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t j = rank[i];
-  double* acc_t = acc_buf(sel);
-  const double a0 = acc_t[3 * j + 0], a1 = acc_t[3 * j + 1], a2 = acc_t[3 * j + 2];
-  const double v0 = __dadd_rn(vel.p[0][i], __dmul_rn(dt, a0));  // b.v[k] += dt * a[k]   (:650-652)
-  const double v1 = __dadd_rn(vel.p[1][i], __dmul_rn(dt, a1));
-  const double v2 = __dadd_rn(vel.p[2][i], __dmul_rn(dt, a2));
-  vel.p[0][i] = v0;
-  vel.p[1][i] = v1;
-  vel.p[2][i] = v2;
-  const double x = __dadd_rn(pos.p[0][i], __dmul_rn(dt, v0));  // dx = dt*v; p += dx     (:653-658)
-  const double y = __dadd_rn(pos.p[1][i], __dmul_rn(dt, v1));
-  const double z = __dadd_rn(pos.p[2][i], __dmul_rn(dt, v2));
-  pos.p[0][i] = x;
-  pos.p[1][i] = y;
-  pos.p[2][i] = z;
-  pm[i].x = x;  // AoS mirror read by the next build
-  pm[i].y = y;
-  pm[i].z = z;
-}
-
-// a[k] = 0 (:659-661), coalesced over the buffer the kick just consumed
-__global__ void __launch_bounds__(256) zero_acc_kernel(AccSel sel, uint64_t count) {
-  pdl_sync();
-  double* acc_t = acc_buf(sel);
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
-    acc_t[i] = 0.0;
+  const bool valid = i < n;
+  double x = 0.0, y = 0.0, z = 0.0;
+  if (valid) {
+    // every load of the particle before its first store: the arrays are not provably disjoint for the compiler, so a
+    // store in between would order the later loads behind it (five dependent round trips instead of two)
+    double* acc_t = acc_buf(sel);
+    const uint64_t j = rank[i];
+    const double u0 = vel.p[0][i], u1 = vel.p[1][i], u2 = vel.p[2][i];
+    const double p0 = pos.p[0][i], p1 = pos.p[1][i], p2 = pos.p[2][i];
+    const double a0 = acc_t[3 * j + 0], a1 = acc_t[3 * j + 1], a2 = acc_t[3 * j + 2];
+    const double v0 = __dadd_rn(u0, __dmul_rn(dt, a0));  // b.v[k] += dt * a[k]   (:650-652)
+    const double v1 = __dadd_rn(u1, __dmul_rn(dt, a1));
+    const double v2 = __dadd_rn(u2, __dmul_rn(dt, a2));
+    x = __dadd_rn(p0, __dmul_rn(dt, v0));  // dx = dt*v; p += dx     (:653-658)
+    y = __dadd_rn(p1, __dmul_rn(dt, v1));
+    z = __dadd_rn(p2, __dmul_rn(dt, v2));
+    acc_t[3 * j + 0] = 0.0;  // a[k] = 0 (:659-661)
+    acc_t[3 * j + 1] = 0.0;
+    acc_t[3 * j + 2] = 0.0;
+    vel.p[0][i] = v0;
+    vel.p[1][i] = v1;
+    vel.p[2][i] = v2;
+    pos.p[0][i] = x;
+    pos.p[1][i] = y;
+    pos.p[2][i] = z;
+    pm[i].x = x;  // AoS mirror read by the next build
+    pm[i].y = y;
+    pm[i].z = z;
+  }
+  accumulate_extent(x, y, z, valid, 2u, ss, sm);  // (2: the masses did not change, sort_prep keeps what the upload found)
 }
 
 int kick_drift(Ctx* c, double dt) {
   const uint32_t n = (uint32_t)c->n;
   V3 pos = {{c->pos[0], c->pos[1], c->pos[2]}}, vel = {{c->vel[0], c->vel[1], c->vel[2]}};
-  KDNB_LAUNCH(c, kick_drift_kernel, (n + 255) / 256, 256, 0, n, dt, pos, vel, c->rank, acc_sel(c), c->pm);
-  if (c->p2p_on) {
-    KDNB_LAUNCH(c, zero_acc_kernel, 1184, 256, 0, acc_sel(c), 3ull * c->n);
-  } else {
-    KDNB_CUDA_TRY(c, cudaMemsetAsync(c->acc_t, 0, 3ull * c->n * sizeof(double), c->stream));
-  }
+  KDNB_LAUNCH(c, kick_drift_kernel, (n + 255) / 256, 256, 0, n, dt, pos, vel, c->rank, acc_sel(c), c->pm, c->sort_state);
   KDNB_CHECK_LAUNCH(c);
+  c->extent_fresh = true;
   c->tree_valid = false;  // positions moved: the tree no longer describes them
   return 0;
 }
 
+// the extent records start empty before a new particle set is converted
+__global__ void __launch_bounds__(EXT_PARTS) extent_reset_kernel(uint64_t* ss) {
+  pdl_sync();
+  uint64_t* rec = ss + SS_PART + 8 * threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) rec[j] = j < 3 ? ~0ull : 0ull;
+}
+
 __global__ void __launch_bounds__(256) aos_to_soa_kernel(uint32_t n, const kdnb_particle* __restrict__ aos, V3 pos,
                                                          V3 vel, double* __restrict__ radius,
-                                                         double* __restrict__ mass, PosM* __restrict__ pm) {
+                                                         double* __restrict__ mass, PosM* __restrict__ pm,
+                                                         uint64_t* __restrict__ ss) {
   pdl_sync();
+  __shared__ uint64_t sm[8][8];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double2* q = reinterpret_cast<const double2*>(aos + i);
-  const double2 a = q[0], b = q[1], c2 = q[2], d = q[3];
-  pos.p[0][i] = a.x;
-  pos.p[1][i] = a.y;
-  pos.p[2][i] = b.x;
-  vel.p[0][i] = b.y;
-  vel.p[1][i] = c2.x;
-  vel.p[2][i] = c2.y;
-  radius[i] = d.x;
-  mass[i] = d.y;
-  PosM rec;
-  rec.x = a.x;
-  rec.y = a.y;
-  rec.z = b.x;
-  rec.m = d.y;
-  pm[i] = rec;
+  const bool valid = i < n;
+  double x = 0.0, y = 0.0, z = 0.0;
+  uint32_t light = 0u;
+  if (valid) {
+    const double2* q = reinterpret_cast<const double2*>(aos + i);
+    const double2 a = q[0], b = q[1], c2 = q[2], d = q[3];
+    x = a.x, y = a.y, z = b.x;
+    pos.p[0][i] = a.x;
+    pos.p[1][i] = a.y;
+    pos.p[2][i] = b.x;
+    vel.p[0][i] = b.y;
+    vel.p[1][i] = c2.x;
+    vel.p[2][i] = c2.y;
+    radius[i] = d.x;
+    mass[i] = d.y;
+    PosM rec;
+    rec.x = a.x;
+    rec.y = a.y;
+    rec.z = b.x;
+    rec.m = d.y;
+    pm[i] = rec;
+    light = (d.y > 0.0) ? 0u : 1u;
+  }
+  accumulate_extent(x, y, z, valid, light, ss, sm);
 }
 
 __global__ void __launch_bounds__(256) soa_to_aos_kernel(uint32_t n, kdnb_particle* __restrict__ aos, V3 pos, V3 vel,
@@ -117,8 +138,10 @@ __global__ void __launch_bounds__(256) soa_to_aos_kernel(uint32_t n, kdnb_partic
 int aos_to_soa(Ctx* c) {
   const uint32_t n = (uint32_t)c->n;
   V3 pos = {{c->pos[0], c->pos[1], c->pos[2]}}, vel = {{c->vel[0], c->vel[1], c->vel[2]}};
-  KDNB_LAUNCH(c, aos_to_soa_kernel, (n + 255) / 256, 256, 0, n, c->aos, pos, vel, c->radius, c->mass, c->pm);
+  KDNB_LAUNCH(c, extent_reset_kernel, 1, EXT_PARTS, 0, c->sort_state);
+  KDNB_LAUNCH(c, aos_to_soa_kernel, (n + 255) / 256, 256, 0, n, c->aos, pos, vel, c->radius, c->mass, c->pm, c->sort_state);
   KDNB_CHECK_LAUNCH(c);
+  c->extent_fresh = true;
   return 0;
 }
 

@@ -29,9 +29,7 @@ struct Pos3 {
   const double* p[3];
 };
 
-// sort state (device): [0..2] min key64, [3..5] max key64 (flat_detect), [6..8] lo, [9..11] scale as f64 bits
-// (sort_prep), [12] need64
-constexpr int SS_MIN = 0, SS_MAX = 3, SS_LO = 6, SS_SCALE = 9, SS_NEED64 = 12, SS_WORDS = 16;
+// (sort state layout: common.cuh)
 
 __device__ __forceinline__ double key_to_f64(uint64_t k) {  // inverse of f64_key
   const uint64_t u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
@@ -229,70 +227,56 @@ __global__ void __launch_bounds__(SORT_THREADS, 8) sort_downsweep(Pos3 pos, cons
   }
 }
 
-// flat[d] = 1 when every particle has the same coordinate d (planar inputs: the reference's ring has z == 0 for
-// ever).  Such a dimension has extent 0 in every node, so it is never the split dimension (array_kd_tree.rs:551-556
-// keeps the lower dimension on ties) and its sorted list is never consulted: sorting and partitioning it is skipped.
-// Dimension 0 is always kept — it is the tie winner when all extents are 0 and it orders the leaves.
-__global__ void flat_init(uint32_t* flat, uint64_t* ss) {
+// sort_prep (one CTA) reduces — and resets — the extent records that the kernel which last wrote the positions
+// accumulated (aos_to_soa, kick_drift: accumulate_extent, common.cuh):
+//  * lo / scale of the 32-bit keys; non-finite extremes (inf or NaN coordinates) go straight to the 64-bit sort;
+//  * flat[d] = 1 when every particle has the same coordinate d, i.e. min == max (planar inputs: the reference's ring has
+//    z == 0 for ever).  Such a dimension has extent 0 in every node, so it is never the split dimension
+//    (array_kd_tree.rs:551-556 keeps the lower dimension on ties) and its sorted list is never consulted: sorting and
+//    partitioning it is skipped.  Dimension 0 is always kept — it is the tie winner when all extents are 0 and it
+//    orders the leaves;
+//  * flat[3] = 1 when, in addition, every z is +-0 and every mass is > 0 (the masses are seen at upload only): then every node's centre-of-mass z (sum m*z / sum m) is +-0 as well, dz == 0 in every test and
+//    interaction, and the walk skips the z terms (walk2.cuh).
+__global__ void __launch_bounds__(EXT_PARTS) sort_prep(uint64_t* ss, uint32_t* flat) {
   pdl_sync();
-  if (threadIdx.x < 4) flat[threadIdx.x] = threadIdx.x > 0 ? 1u : 0u;
-  if (threadIdx.x < 3) {
-    ss[SS_MIN + threadIdx.x] = ~0ull;
-    ss[SS_MAX + threadIdx.x] = 0ull;
-  }
-  if (threadIdx.x == 0) ss[SS_NEED64] = 0ull;
-}
-// flat[3] = 1 when, in addition, every z is +-0 and every mass is > 0: then every node's centre-of-mass z
-// (sum m*z / sum m) is +-0 as well, dz == 0 in every test and interaction, and the walk skips the z terms (walk2.cuh).
-// The same pass reduces the extreme keys of every dimension (the range the 32-bit sort keys are scaled to).
-__global__ void __launch_bounds__(256) flat_detect(Pos3 pos, const double* __restrict__ mass, uint32_t n,
-                                                   uint32_t* __restrict__ flat, uint64_t* __restrict__ ss) {
-  pdl_sync();
-  __shared__ uint64_t smin[8], smax[8];
-  const int d = blockIdx.y;
-  const uint64_t k0 = f64_key(pos.p[d][0]);
-  bool differs = false, heavy = true;
-  uint64_t kmin = ~0ull, kmax = 0ull;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint64_t k = f64_key(pos.p[d][i]);
-    differs |= k != k0;
-    kmin = k < kmin ? k : kmin;
-    kmax = k > kmax ? k : kmax;
-    if (d == 2) heavy &= mass[i] > 0.0;
-  }
-  if (d > 0 && differs) flat[d] = 0u;
-  if (d == 2 && (differs || !heavy || k0 != f64_key(0.0))) flat[3] = 0u;
+  __shared__ uint64_t sm[8][8];
+  uint64_t v[7];
+  {
+    uint64_t* rec = ss + SS_PART + 8 * threadIdx.x;  // one record per thread
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const uint64_t a = __shfl_xor_sync(0xffffffffu, kmin, o), b = __shfl_xor_sync(0xffffffffu, kmax, o);
-    kmin = a < kmin ? a : kmin;
-    kmax = b > kmax ? b : kmax;
+    for (int j = 0; j < 7; ++j) {
+      v[j] = rec[j];
+      rec[j] = j < 3 ? ~0ull : 0ull;
+    }
   }
-  if ((threadIdx.x & 31) == 0) smin[threadIdx.x >> 5] = kmin, smax[threadIdx.x >> 5] = kmax;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const uint64_t r = j < 3 ? warp_min_u64(v[j]) : warp_max_u64(v[j]);
+    if (lane == 0) sm[w][j] = r;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int k = 1; k < 8; ++k) {
-      kmin = smin[k] < kmin ? smin[k] : kmin;
-      kmax = smax[k] > kmax ? smax[k] : kmax;
+    uint64_t t[7];
+    for (int j = 0; j < 7; ++j) {
+      t[j] = sm[0][j];
+      for (int q = 1; q < 8; ++q) t[j] = j < 3 ? (sm[q][j] < t[j] ? sm[q][j] : t[j]) : (sm[q][j] > t[j] ? sm[q][j] : t[j]);
     }
-    atomicMin(reinterpret_cast<unsigned long long*>(&ss[SS_MIN + d]), (unsigned long long)kmin);
-    atomicMax(reinterpret_cast<unsigned long long*>(&ss[SS_MAX + d]), (unsigned long long)kmax);
+    uint64_t need64 = 0ull;
+    for (int d = 0; d < 3; ++d) {
+      const double lo = key_to_f64(t[d]), hi = key_to_f64(t[3 + d]);
+      double scale = 0.0;  // all keys 0 when the extent is 0: one run of equal coordinates, already in id order
+      if (!(fabs(lo) <= 1.7976931348623157e308) || !(fabs(hi) <= 1.7976931348623157e308)) need64 = 1ull;
+      else if (hi > lo) scale = 4294967295.0 / (hi - lo);  // (hi - lo) may overflow to inf: scale 0, handled like extent 0 + fix-up
+      ss[SS_LO + d] = (uint64_t)__double_as_longlong(lo);
+      ss[SS_SCALE + d] = (uint64_t)__double_as_longlong(scale);
+      flat[d] = (d > 0 && t[d] == t[3 + d]) ? 1u : 0u;
+    }
+    ss[SS_NEED64] = need64;
+    if (t[6] < 2ull) ss[SS_LIGHT] = t[6];  // an upload's records (a kick leaves 2: the masses did not change)
+    const uint64_t light = ss[SS_LIGHT];
+    flat[3] = (t[2] == t[5] && t[2] == f64_key(0.0) && light == 0ull) ? 1u : 0u;
   }
-}
-// lo / scale of the 32-bit keys; non-finite extremes (inf or NaN coordinates) go straight to the 64-bit sort
-__global__ void sort_prep(uint64_t* ss) {
-  pdl_sync();
-  const int d = threadIdx.x;
-  if (d >= 3) return;
-  const double lo = key_to_f64(ss[SS_MIN + d]), hi = key_to_f64(ss[SS_MAX + d]);
-  double scale = 0.0;  // all keys 0 when the extent is 0: one run of equal coordinates, already in id order
-  if (!(fabs(lo) <= 1.7976931348623157e308) || !(fabs(hi) <= 1.7976931348623157e308)) {
-    ss[SS_NEED64] = 1ull;
-  } else if (hi > lo) {
-    scale = 4294967295.0 / (hi - lo);  // (hi - lo) may overflow to inf: scale 0, handled like extent 0 + fix-up
-  }
-  ss[SS_LO + d] = (uint64_t)__double_as_longlong(lo);
-  ss[SS_SCALE + d] = (uint64_t)__double_as_longlong(scale);
 }
 
 // Orders every run of equal key32 by (key64, id).  The 32-bit sort left each run in ascending id order, so a run is
@@ -461,10 +445,10 @@ int sort_lists(Ctx* c) {
   static const char* knob = getenv("KDNB_SORT");
   static const bool only64 = knob && std::string(knob) == "64";
   static const bool stubs = knob && std::string(knob) == "stubs";
-  KDNB_LAUNCH(c, flat_init, 1, 32, 0, c->flat, c->sort_state);
-  KDNB_LAUNCH(c, flat_detect, dim3(std::min<uint32_t>((n + 255) / 256, 1184u), 3), 256, 0, pos, c->mass, n, c->flat,
-              c->sort_state);
-  KDNB_LAUNCH(c, sort_prep, 1, 32, 0, c->sort_state);
+  // key scaling and flat / planar flags from the extents accumulated by whoever wrote the positions (upload or the
+  // previous kick); a rebuild on unchanged positions keeps what the previous build derived
+  if (c->extent_fresh) KDNB_LAUNCH(c, sort_prep, 1, EXT_PARTS, 0, c->sort_state, c->flat);
+  c->extent_fresh = false;
   if (only64) {
     sort_passes<uint64_t>(c, pos, false);
   } else {

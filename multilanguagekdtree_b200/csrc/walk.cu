@@ -1,11 +1,10 @@
 // walk.cu — theta-criterion force walk, calc_accel / accel_recur of the reference
 // (Parallel/RustVersion/src/array_kd_tree.rs:585-621) with calc_pp_accel (array_particle.rs:67-76) in the leaves:
-// host-side launch logic, the peer-exchange wait kernel, and the kernels themselves (walk_legacy.cuh).
+// host-side launch logic, the peer-exchange wait kernel, and the kernels themselves (walk2.cuh).
 #include <cstdlib>
 
 #include "ctx.cuh"
 #include "walk2.cuh"
-#include "walk_legacy.cuh"
 
 namespace kdnb {
 
@@ -32,30 +31,6 @@ int p2p_wait_step(Ctx* c) {
   KDNB_LAUNCH(c, p2p_wait_kernel, 1, 32, 0, c->p2p_state, c->world);
   KDNB_CHECK_LAUNCH(c);
   return 0;
-}
-
-template <int PPL, int MINB, int WALK_THREADS = 64, int DW = 4>
-static void launch_walk(Ctx* c, uint32_t begin, uint32_t end) {
-  constexpr int WALK_WARPS = WALK_THREADS / 32;
-  const uint32_t groups = (end - begin + 32 * PPL - 1) / (32 * PPL);
-  const uint32_t grid = std::max<uint32_t>((groups + WALK_WARPS - 1) / WALK_WARPS, 1u);
-  const bool counts = (c->flags & KDNB_FLAG_WALK_COUNTS) != 0;
-  const bool exact = (c->flags & KDNB_FLAG_EXACT_MATH) != 0;
-  P2P pp = c->p2p;
-  if (!c->p2p_on) pp.world = 0;
-#define KDNB_WALK_ARGS c->nodes, c->posm, c->acc_t, begin, end, c->theta2, c->wcounts, pp
-  const bool peer = pp.world > 1;
-  if (exact && counts)
-    KDNB_LAUNCH(c, (walk_kernel<PPL, WALK_THREADS, 1, true, true, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
-  else if (exact)
-    KDNB_LAUNCH(c, (walk_kernel<PPL, WALK_THREADS, 1, true, false, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
-  else if (counts)
-    KDNB_LAUNCH(c, (walk_kernel<PPL, WALK_THREADS, 1, false, true, true>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
-  else if (peer)
-    KDNB_LAUNCH(c, (walk_kernel<PPL, WALK_THREADS, MINB, false, false, true, DW>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
-  else
-    KDNB_LAUNCH(c, (walk_kernel<PPL, WALK_THREADS, MINB, false, false, false, DW>), grid, WALK_THREADS, 0, KDNB_WALK_ARGS);
-#undef KDNB_WALK_ARGS
 }
 
 static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
@@ -129,14 +104,14 @@ int walk(Ctx* c) {
   // nothing to walk but raises this rank's flag on every peer; without it all ranks would wait for the flag until the
   // wait kernel's timeout, every step)
   if (end > begin || (c->world > 1 && c->p2p_on)) {
-    static const int cfg = [] {
-      const char* s = getenv("KDNB_WALK_CFG");  // profiling knob: 0 = walk2 (default), anything else = the previous kernel
-      return s ? atoi(s) : 0;
-    }();
-    switch (cfg) {
-      case 0: launch_walk2(c, begin, end); break;
-      default: launch_walk<1, 32, 32>(c, begin, end); break;  // the previous kernel (walk_legacy.cuh), for A/B timing
+#ifdef KDNB_WALK_AB  // development experiments only (-DKDNB_WALK_AB): KDNB_WALK_DBG=1 skips the drains, =2 doubles them
+    {
+      static const int dbg = [] { const char* s = getenv("KDNB_WALK_DBG"); return s ? atoi(s) : 0; }();
+      static bool set = false;
+      if (!set) cudaMemcpyToSymbol(w2_dbg, &dbg, sizeof(int)), set = true;
     }
+#endif
+    launch_walk2(c, begin, end);
     KDNB_CHECK_LAUNCH(c);
   }
   c->acc_valid = true;

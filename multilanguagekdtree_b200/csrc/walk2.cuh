@@ -1,22 +1,22 @@
-// walk2.cuh — the walk kernel that runs by default (launched from walk.cu).
+// walk2.cuh — the walk kernel (launched from walk.cu).
 //
 // theta-criterion force walk, calc_accel / accel_recur of the reference
 // (Parallel/RustVersion/src/array_kd_tree.rs:585-621) with calc_pp_accel (array_particle.rs:67-76) in the leaves.
 //
-// One warp (= one CTA, 32 CTAs per SM) owns 32 consecutive TREE-ORDERED particles (a compact patch of ~4 leaves), one
+// One warp (= one CTA, 24 CTAs per SM) owns 32 consecutive TREE-ORDERED particles (a compact patch of ~4 leaves), one
 // per lane, and keeps a shared-memory stack of frontier entries (node, lane mask).  Per round it pops up to 32
 // entries and classifies them ONE NODE PER LANE against the bounding box of the 32 particles:
 //   far   : size^2 <  theta^2 * dmin^2 * (1 - 1e-9)  -> every particle in the entry's mask accepts the node
 //   near  : size^2 >= theta^2 * dmax^2 * (1 + 1e-9)  -> every particle opens it
 //   mixed : otherwise -> the reference's test is evaluated per particle (below)
 //   leaf  : its particles become pair interactions
-// dmin/dmax are the distances from the node's centre of mass to the box; the 1e-9 margin dwarfs the <= 1e-15
-// rounding of either side, so "far"/"near" provably agree with the reference's per-particle test
+// dmin/dmax bound the distances from the node's centre of mass to the box from below / above (box_bounds()); the
+// 1e-9 margin dwarfs the rounding of either side, so "far"/"near" provably agree with the reference's per-particle test
 //       size*size < (THETA*THETA) * dist_sqr            (array_kd_tree.rs:606)
-// Mixed nodes of a batch are parked in shared memory ({cm, size^2}, one slot per owning lane); the warp then runs over
-// them with ONE PARTICLE PER LANE evaluating exactly that test with the reference's unfused operation order (:601-606),
-// and a ballot hands the accept mask back to the owning lane.  After that the batch is finished one node per lane
-// again: far + accepted monopoles are appended to the interaction list with their lane masks, near + still-open
+// Mixed nodes of a batch are parked in shared memory ({cm, size^2}, compacted); the warp then runs over them with ONE
+// PARTICLE PER LANE evaluating exactly that test with the reference's unfused operation order (:601-606), and a ballot
+// per node — left in shared memory for the owning lane — is the accept mask.  After that the batch is finished one node
+// per lane again: far + accepted monopoles are appended to the interaction list with their lane masks, near + still-open
 // nodes push both children.  Every particle thus accepts / opens precisely the nodes the reference's recursion does
 // (checked by KDNB_FLAG_WALK_COUNTS against the oracle: per-particle counts of tests, accepts, leaf visits and pair
 // interactions are identical).  Leaves of a batch are queued and expanded 32/LP leaves at a time (LP lanes per leaf):
@@ -25,117 +25,168 @@
 //
 // Why this shape: on B200 an FP64 warp instruction holds its scheduler's issue port for two cycles and nothing
 // else issues in its shadow (tools/issue_probe.cu: 16 DFMA = 35 cycles, every extra ALU instruction +1 cycle), so the
-// kernel is bound by  2.19 * FP64 instructions + other instructions.  The first version of this kernel handled mixed
-// nodes and leaves one at a time with shuffles (~90 issue cycles per mixed node, ~60 per leaf: 30 % of all
-// instructions, profiles/README.md); here a mixed node costs 10 FP64 + ~11 other instructions and a leaf ~8.
+// kernel is bound by  ~2 * FP64 instructions + other instructions  (profiles/README.md: the ncu instruction counts
+// reproduce the measured time), and every change is judged by the instructions it removes.
 //
-// Forces are not evaluated during the traversal: the interaction list is drained by a branch-free, 4-way unrolled
-// loop, 16 FP64 + 7 other instructions per interaction (broadcast shared-memory loads, no global loads).  When every
-// z coordinate is +-0 and every mass is > 0 (flat[3], set by flat_detect in sort.cu — the reference's own initial
-// conditions, circular_orbits, array_particle.rs:19-44, are planar for ever) all centre-of-mass z are +-0 too, dz is
-// exactly 0 in every interaction and every test, and the z terms are skipped (13 FP64 per interaction): the
+// Forces are not evaluated during the traversal: the interaction list is drained by a branch-free loop over blocks of
+// four interactions (W2Blk: one base register, seven 16-byte broadcast loads), 13 FP64 + 6 other instructions per
+// interaction on planar inputs.  When every z coordinate is +-0 and every mass is > 0 (flat[3], sort.cu: sort_prep —
+// the reference's own initial conditions, circular_orbits, array_particle.rs:19-44, are planar for ever) all
+// centre-of-mass z are +-0 too, dz is exactly 0 in every interaction and every test, and the z terms are skipped: the
 // results are bit-identical to the general path, az stays +0.
 //
 // Accumulation is a running f64 sum per particle (the reference combines pairwise along the recursion, :611-613);
 // the difference is summation order only and is covered by the stated 1e-12 tolerance.
 #pragma once
-#include "walk_legacy.cuh"
+#include "ctx.cuh"
 
 namespace kdnb {
 
 constexpr int W2_STACK = 320;  // soft capacity: batches shrink as the stack fills
 constexpr int W2_SLACK = 32;   // depth-first tail when the stack is at capacity (tree depth <= 27 at 1e8 particles)
-constexpr int W2_LIST = 96;    // interaction-list capacity (appends come in groups of <= 32)
+constexpr int W2_LIST = 96;    // interaction-list capacity (appends come in groups of <= 32); multiple of 4
 
-// 1.875 = the e^2 coefficient of (1 - e)^(-3/2); read from the constant bank as an instruction operand (as a literal
-// it costs two register moves per loop iteration at the 64-register budget)
+// 1.875 = the e^2 coefficient of (1 - e)^(-3/2)
 __constant__ double W2_C2 = 1.875;
 
-template <bool EXACT>
-struct W2Smem {
-  uint32_t snode[W2_STACK + W2_SLACK];
-  uint32_t smask[W2_STACK + W2_SLACK];
-  double lx[W2_LIST], ly[W2_LIST], lz[W2_LIST], lm[W2_LIST];  // monopoles / leaf particles, SoA: the drain loop reads
-  uint32_t lmask[W2_LIST];                                     // four consecutive interactions with 16-byte loads
-  uint32_t lflag[EXACT ? W2_LIST : 4];  // 1 = leaf particle (the exact-math formulas differ, see interact<>)
-  union {
-    Rec32 mix[32];  // {cx, cy, cz, size^2} of the batch's mixed nodes, slot = owning lane
-    uint4 lq[32];   // {first slot, num_parts, lane mask, -} of the batch's leaves, compacted
-  };
+struct __align__(32) Rec32 {
+  double a, b, c, d;
 };
 
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// four consecutive list entries: monopoles {cm, m} or leaf particles {p, m}, their lane masks, and (exact-math
+// contexts only) 1 = leaf particle.  128 bytes, so that the drain loop addresses everything off one base register.
+struct __align__(16) W2Blk {
+  double x[4], y[4], m[4];
+  uint32_t mask[4];
+  uint32_t flag[4];
+};
+static_assert(sizeof(W2Blk) == 128, "W2Blk");
+
+struct W2Smem {
+  W2Blk blk[W2_LIST / 4];
+  double lz[W2_LIST];  // z of the list entries (general inputs only)
+  uint32_t snode[W2_STACK + W2_SLACK];
+  uint32_t smask[W2_STACK + W2_SLACK];
+  union {
+    Rec32 mix[32];  // {cx, cy, cz, size^2} of the batch's mixed nodes, compacted
+    uint4 lq[32];   // {first slot, num_parts, lane mask, -} of the batch's leaves, compacted
+  };
+  uint32_t mres[32];   // accept ballots of the batch's mixed nodes
+  uint32_t mixmk[32];  // their entry masks (walk counters only)
+};
+
+// the reference's formulas (KDNB_FLAG_EXACT_MATH): node -m / (dist_sqr * dist) (array_kd_tree.rs:608), particle
+// -m / (dist*dist*dist) (array_particle.rs:72), IEEE sqrt and divide, unfused
+__device__ __forceinline__ void interact_exact(double ex, double ey, double ez, double em, bool use, bool is_particle,
+                                               double px, double py, double pz, double& ax, double& ay, double& az) {
+  if (use) {
+    const double dx = __dsub_rn(px, ex), dy = __dsub_rn(py, ey), dz = __dsub_rn(pz, ez);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    const double dist = __dsqrt_rn(d2);
+    const double den = is_particle ? __dmul_rn(__dmul_rn(dist, dist), dist) : __dmul_rn(d2, dist);
+    const double magi = __ddiv_rn(-em, den);
+    ax = __dadd_rn(ax, __dmul_rn(magi, dx));
+    ay = __dadd_rn(ay, __dmul_rn(magi, dy));
+    az = __dadd_rn(az, __dmul_rn(magi, dz));
+  }
+}
+
 // all lanes stream over the list; lane = particle
+#ifdef KDNB_WALK_AB
+__device__ int w2_dbg;  // development experiments: 1 = skip the drains, 2 = drain every list twice
+#endif
 template <bool EXACT, bool FLATZ>
-__device__ __forceinline__ void drain2(W2Smem<EXACT>& S, int cnt, int lane, double px, double py, double pz, double& ax,
+__device__ __forceinline__ void drain2(W2Smem& S, int cnt, int lane, double px, double py, double pz, double& ax,
                                        double& ay, double& az) {
   __syncwarp();
+#ifdef KDNB_WALK_AB
+  const int dbg = w2_dbg;
+  if (dbg == 1) return;
+  for (int rep = 0; rep < (dbg == 2 ? 2 : 1); ++rep)
+#endif
   if (EXACT) {
     for (int i = 0; i < cnt; ++i) {
-      Rec32 e;
-      e.a = S.lx[i], e.b = S.ly[i], e.c = S.lz[i], e.d = S.lm[i];
-      const bool use = (S.lmask[i] >> lane) & 1u;
-      interact<true>(e, use, S.lflag[i] != 0, px, py, pz, ax, ay, az);
+      const W2Blk& B = S.blk[i >> 2];
+      const int s = i & 3;
+      interact_exact(B.x[s], B.y[s], S.lz[i], B.m[s], (B.mask[s] >> lane) & 1u, B.flag[s] != 0, px, py, pz, ax, ay, az);
     }
   } else {
-    constexpr int DW = 4;
-    // DW interactions in lock-step, interleaved stage by stage; the list is padded to a multiple of DW with
-    // masked-out entries.  A masked-out lane zeroes the rsqrt estimate (one 32-bit select: MUFU.RSQ64H leaves the low
-    // word 0), which makes its contribution exactly -0 * d = no-op and also absorbs d2 == 0 (inf estimate).
+    // -m d / r^3 without divide or sqrt: y0 = MUFU.RSQ64H estimate (rel. error < 2^-22), e = 1 - d2*y0^2,
+    // r^-3 = y0^3 (1 - e)^(-3/2) = y0^3 (1 + 1.5 e + 1.875 e^2 + O(e^3)), O(e^3) < 2^-63.  Four interactions in
+    // lock-step, interleaved stage by stage; the list is padded to whole blocks with masked-out entries.  A masked-out
+    // lane zeroes the estimate (one 32-bit select on its high word; the low word of an estimate is 0), which makes its
+    // contribution exactly -0 * d = no-op and also absorbs d2 == 0 (inf estimate).  (Predicating the accumulating FMAs
+    // instead does not pay: ptxas turns a predicated DFMA into DFMA + two FSEL.)
     const uint32_t lanebit = 1u << lane;
-    const int padded = (cnt + DW - 1) / DW * DW;
-    if (lane < padded - cnt) {
-      S.lx[cnt + lane] = S.ly[cnt + lane] = S.lz[cnt + lane] = S.lm[cnt + lane] = 0.0;
-      S.lmask[cnt + lane] = 0u;
+    const int nblk = (cnt + 3) >> 2;
+    if (lane < 4 * nblk - cnt) {
+      const int i = cnt + lane;
+      W2Blk& B = S.blk[i >> 2];
+      B.x[i & 3] = B.y[i & 3] = B.m[i & 3] = 0.0;
+      B.mask[i & 3] = 0u;
+      if (!FLATZ) S.lz[i] = 0.0;
     }
     __syncwarp();
-    for (int i = 0; i < padded; i += DW) {
-      double dx[DW], dy[DW], dz[DW], d2[DW], y[DW], y2[DW], ee[DW], mq[DW], q[DW];
-      const uint4 m4 = *reinterpret_cast<const uint4*>(&S.lmask[i]);
+    const double* lz = S.lz;
+    for (const W2Blk *B = S.blk, *E = S.blk + nblk; B != E; ++B, lz += 4) {
+      double dx[4], dy[4], dz[4], d2[4], y[4], y2[4], ee[4], mq[4], q[4];
+      const uint4 m4 = *reinterpret_cast<const uint4*>(B->mask);
       const uint32_t use[4] = {m4.x & lanebit, m4.y & lanebit, m4.z & lanebit, m4.w & lanebit};
 #pragma unroll
-      for (int j = 0; j < DW; j += 2) {
-        const double2 ex = *reinterpret_cast<const double2*>(&S.lx[i + j]);
-        const double2 ey = *reinterpret_cast<const double2*>(&S.ly[i + j]);
-        const double2 em = *reinterpret_cast<const double2*>(&S.lm[i + j]);
+      for (int j = 0; j < 4; j += 2) {
+        const double2 ex = *reinterpret_cast<const double2*>(&B->x[j]);
+        const double2 ey = *reinterpret_cast<const double2*>(&B->y[j]);
+        const double2 em = *reinterpret_cast<const double2*>(&B->m[j]);
         dx[j] = __dsub_rn(px, ex.x), dx[j + 1] = __dsub_rn(px, ex.y);
         dy[j] = __dsub_rn(py, ey.x), dy[j + 1] = __dsub_rn(py, ey.y);
         if (!FLATZ) {
-          const double2 ez = *reinterpret_cast<const double2*>(&S.lz[i + j]);
+          const double2 ez = *reinterpret_cast<const double2*>(&lz[j]);
           dz[j] = __dsub_rn(pz, ez.x), dz[j + 1] = __dsub_rn(pz, ez.y);
         }
         mq[j] = -em.x, mq[j + 1] = -em.y;
       }
 #pragma unroll
-      for (int j = 0; j < DW; ++j) d2[j] = __dmul_rn(dx[j], dx[j]);
+      for (int j = 0; j < 4; ++j) d2[j] = __dmul_rn(dx[j], dx[j]);
 #pragma unroll
-      for (int j = 0; j < DW; ++j) d2[j] = fma(dy[j], dy[j], d2[j]);
+      for (int j = 0; j < 4; ++j) d2[j] = fma(dy[j], dy[j], d2[j]);
       if (!FLATZ) {
 #pragma unroll
-        for (int j = 0; j < DW; ++j) d2[j] = fma(dz[j], dz[j], d2[j]);
+        for (int j = 0; j < 4; ++j) d2[j] = fma(dz[j], dz[j], d2[j]);
       }
 #pragma unroll
-      for (int j = 0; j < DW; ++j) {
+      for (int j = 0; j < 4; ++j) {
         const double r = rsqrt_estimate(d2[j]);
         y[j] = __hiloint2double(use[j] ? __double2hiint(r) : 0, 0);
       }
 #pragma unroll
-      for (int j = 0; j < DW; ++j) y2[j] = __dmul_rn(y[j], y[j]);
+      for (int j = 0; j < 4; ++j) y2[j] = __dmul_rn(y[j], y[j]);
 #pragma unroll
-      for (int j = 0; j < DW; ++j) {
+      for (int j = 0; j < 4; ++j) {
         ee[j] = fma(-d2[j], y2[j], 1.0);
         y[j] = __dmul_rn(y[j], y2[j]);  // y0^3
       }
 #pragma unroll
-      for (int j = 0; j < DW; ++j) {
+      for (int j = 0; j < 4; ++j) {
         q[j] = fma(W2_C2, ee[j], 1.5);
         mq[j] = __dmul_rn(mq[j], y[j]);  // -m * y0^3
       }
 #pragma unroll
-      for (int j = 0; j < DW; ++j) ee[j] = __dmul_rn(mq[j], ee[j]);
+      for (int j = 0; j < 4; ++j) ee[j] = __dmul_rn(mq[j], ee[j]);
 #pragma unroll
-      for (int j = 0; j < DW; ++j) mq[j] = fma(ee[j], q[j], mq[j]);
+      for (int j = 0; j < 4; ++j) mq[j] = fma(ee[j], q[j], mq[j]);
 #pragma unroll
-      for (int j = 0; j < DW; ++j) {
+      for (int j = 0; j < 4; ++j) {
         ax = fma(mq[j], dx[j], ax);
         ay = fma(mq[j], dy[j], ay);
         if (!FLATZ) az = fma(mq[j], dz[j], az);
@@ -145,10 +196,22 @@ __device__ __forceinline__ void drain2(W2Smem<EXACT>& S, int cnt, int lane, doub
   __syncwarp();
 }
 
+// store list entry i
+template <bool EXACT, bool FLATZ>
+__device__ __forceinline__ void list_put(W2Smem& S, int i, double x, double y, double z, double m, uint32_t mask,
+                                         uint32_t flag) {
+  W2Blk& B = S.blk[i >> 2];
+  const int s = i & 3;
+  B.x[s] = x, B.y[s] = y, B.m[s] = m;
+  B.mask[s] = mask;
+  if (!FLATZ) S.lz[i] = z;
+  if (EXACT) B.flag[s] = flag;
+}
+
 enum : int { W2_NONE = 0, W2_FAR = 1, W2_NEAR = 2, W2_MIXED = 3, W2_LEAF = 4 };
 
 template <bool EXACT, bool COUNTS, bool PEER, bool FLATZ>
-__device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __restrict__ nodes,
+__device__ __forceinline__ void walk2_body(W2Smem& S, const WNode* __restrict__ nodes,
                                            const PosM* __restrict__ posm, double* __restrict__ acc_t,
                                            uint32_t slot_begin, uint32_t slot_end, double theta2,
                                            unsigned long long* __restrict__ wcounts, const P2P& p2p, int lshift,
@@ -174,10 +237,18 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __rest
     lo[2] = hi[2] = me.z;
   }
   constexpr int ND = FLATZ ? 2 : 3;
+  // Box of the group as centre and half extent.  hs is the half extent INFLATED by 2^-46 of the box's scale: the
+  // distance of a node to the box along one axis is then bounded from below by |c - mid| - hs and from above by
+  // |c - mid| + hs whatever the roundings of mid, hs and the subtractions (each <= 2^-52 of that scale), also where
+  // |c - mid| and hs cancel; relative errors elsewhere are covered by the 1e-9 margins of the far / near tests.
+  double mid[3] = {0.0, 0.0, 0.0}, hs[3] = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int k = 0; k < ND; ++k) {
     lo[k] = warp_min(lo[k]);
     hi[k] = warp_max(hi[k]);
+    mid[k] = 0.5 * lo[k] + 0.5 * hi[k];
+    const double half = 0.5 * hi[k] - 0.5 * lo[k];
+    hs[k] = half + 1.4210854715202004e-14 * (fabs(mid[k]) + half);
   }
   {
     const uint32_t m0 = __ballot_sync(0xffffffffu, valid_p);
@@ -187,48 +258,46 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __rest
     }
   }
   __syncwarp();
-  const double far_margin = 1.0 - 1e-9, near_margin = 1.0 + 1e-9;
+  const double tfar = theta2 * (1.0 - 1e-9), tnear = theta2 * (1.0 + 1e-9);
   const int kmask = (1 << lshift) - 1, lpr = 32 >> lshift;
 
   int ln = 0;
   int sp = warp_has_work ? 1 : 0;
   while (sp > 0) {
-    // ---- pop a batch: lane l takes entry sp+l after the pop (order inside a batch is irrelevant)
+    // ---- pop a batch: lane l takes entry sp+l after the pop (order inside a batch is irrelevant); lanes beyond the
+    // batch re-read its first entry (no divergence, no dead values) and drop out after the classification
     const int room = W2_STACK - sp;
     const int nb = min(min(sp, 32), max(1, room));
     sp -= nb;
     work += 4u;
     const bool has = lane < nb;
-    uint32_t node = 0, na = 0, nbits = 0, mk = 0;
-    int kind = W2_NONE;
-    Rec32 c;
-    c.a = c.b = c.c = c.d = 0.0;
-    double size2 = 0.0;
-    if (has) {
-      node = S.snode[sp + lane];
-      mk = S.smask[sp + lane];
-      const Rec32* rec = reinterpret_cast<const Rec32*>(nodes + node);
-      const int4 info = __ldg(reinterpret_cast<const int4*>(rec + 1));  // size2, (a, b)
-      c = rec[0];  // cx, cy, cz, m (unused for a leaf; loaded alongside so the two sectors travel together)
-      na = (uint32_t)info.z;
-      nbits = (uint32_t)info.w;
-      kind = W2_LEAF;
-      if (nbits & WN_INTERNAL) {
-        size2 = __hiloint2double(info.y, info.x);
-        double dmin2 = 0.0, dmax2 = 0.0;
-        const double cc[3] = {c.a, c.b, c.c};
+    const int at = sp + (has ? lane : 0);
+    const uint32_t node = S.snode[at];
+    const uint32_t mk = S.smask[at];
+    const Rec32* rec = reinterpret_cast<const Rec32*>(nodes + node);
+    const int4 info = __ldg(reinterpret_cast<const int4*>(rec + 1));  // size2, (a, b)
+    const Rec32 c = rec[0];  // cx, cy, cz, m (meaningless for a leaf; loaded alongside so the two sectors travel together)
+    const uint32_t na = (uint32_t)info.z, nbits = (uint32_t)info.w;
+    const double size2 = __hiloint2double(info.y, info.x);
+    int kind;
+    {
+      double dmin2 = 0.0, dmax2 = 0.0;
+      const double cc[3] = {c.a, c.b, c.c};
 #pragma unroll
-        for (int k = 0; k < ND; ++k) {
-          const double below = lo[k] - cc[k], above = cc[k] - hi[k];  // > 0 when the centre is outside the box
-          const double dn = fmax(0.0, fmax(below, above));
-          const double df = fmax(fabs(below), fabs(above));  // = max(|c-lo|, |c-hi|)
-          dmin2 = fma(dn, dn, dmin2);
-          dmax2 = fma(df, df, dmax2);
-        }
-        kind = W2_MIXED;
-        if (size2 < theta2 * dmin2 * far_margin) kind = W2_FAR;
-        else if (size2 >= theta2 * dmax2 * near_margin) kind = W2_NEAR;
+      for (int k = 0; k < ND; ++k) {
+        const double t = fabs(cc[k] - mid[k]);
+        double dn = t - hs[k];
+        // max(dn, 0) on the sign: a negative dn becomes a denormal (high word 0), whose square is 0
+        dn = __hiloint2double(max(__double2hiint(dn), 0), __double2loint(dn));
+        const double df = t + hs[k];
+        dmin2 = fma(dn, dn, dmin2);
+        dmax2 = fma(df, df, dmax2);
       }
+      kind = W2_MIXED;
+      if (size2 < tfar * dmin2) kind = W2_FAR;
+      else if (size2 >= tnear * dmax2) kind = W2_NEAR;
+      if (!(nbits & WN_INTERNAL)) kind = W2_LEAF;
+      if (!has) kind = W2_NONE;
     }
     __syncwarp();
     if (COUNTS) {  // every particle in an entry's mask tests that node (and accepts it when it is far)
@@ -246,15 +315,16 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __rest
     uint32_t omask = kind == W2_NEAR ? mk : 0u;  // lanes that open it
     const uint32_t bal_mixed = __ballot_sync(0xffffffffu, kind == W2_MIXED);
     if (bal_mixed) {
+      const int mrank = __popc(bal_mixed & lt);
       if (kind == W2_MIXED) {
         Rec32 t;
         t.a = c.a, t.b = c.b, t.c = c.c, t.d = size2;
-        S.mix[lane] = t;
+        S.mix[mrank] = t;
+        if (COUNTS) S.mixmk[mrank] = mk;
       }
       __syncwarp();
-      uint32_t am = 0;
-      for (uint32_t rem = bal_mixed; rem; rem &= rem - 1) {
-        const int k = __ffs(rem) - 1;
+      const int nm = __popc(bal_mixed);
+      for (int k = 0; k < nm; ++k) {
         const Rec32 q = S.mix[k];
         const double dx = __dsub_rn(px, q.a), dy = __dsub_rn(py, q.b);
         double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));  // :604, left to right
@@ -264,15 +334,16 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __rest
         }
         const bool accept = q.d < __dmul_rn(theta2, d2);  // :606
         const uint32_t b = __ballot_sync(0xffffffffu, accept);
-        if (lane == k) am = b;
+        if (lane == 0) S.mres[k] = b;
         if (COUNTS) {
-          const uint32_t mk_k = __shfl_sync(0xffffffffu, mk, k);
-          const bool in = (mk_k >> lane) & 1u;
+          const bool in = (S.mixmk[k] >> lane) & 1u;
           cv += in;
           ca += in && accept;
         }
       }
+      __syncwarp();
       if (kind == W2_MIXED) {
+        const uint32_t am = S.mres[mrank];
         amask = am & mk;
         omask = mk & ~am;
       }
@@ -289,12 +360,7 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __rest
           work += (uint32_t)ln;
           ln = 0;
         }
-        if (mine) {
-          const int i = ln + __popc(bal & lt);
-          S.lx[i] = c.a, S.ly[i] = c.b, S.lz[i] = c.c, S.lm[i] = c.d;
-          S.lmask[i] = amask;
-          if (EXACT) S.lflag[i] = 0u;
-        }
+        if (mine) list_put<EXACT, FLATZ>(S, ln + __popc(bal & lt), c.a, c.b, c.c, c.d, amask, 0u);
         ln += add;
       }
     }
@@ -335,12 +401,7 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT>& S, const WNode* __rest
           work += (uint32_t)ln;
           ln = 0;
         }
-        if (valid) {
-          const int i = ln + __popc(bal & lt);
-          S.lx[i] = qv.x, S.ly[i] = qv.y, S.lz[i] = qv.z, S.lm[i] = qv.m;
-          S.lmask[i] = m;
-          if (EXACT) S.lflag[i] = 1u;
-        }
+        if (valid) list_put<EXACT, FLATZ>(S, ln + __popc(bal & lt), qv.x, qv.y, qv.z, qv.m, m, 1u);
         ln += add;
         if (COUNTS) {
           for (int s = 0; s < 32; ++s) {
@@ -408,7 +469,7 @@ walk2_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, dou
              P2P p2p, const uint32_t* __restrict__ flat, int lshift, const uint32_t* __restrict__ gorder,
              uint32_t* __restrict__ gcost) {
   pdl_sync();
-  __shared__ W2Smem<EXACT> S;
+  __shared__ W2Smem S;
   if (!EXACT && !COUNTS && flat[3])
     walk2_body<EXACT, COUNTS, PEER, true>(S, nodes, posm, acc_t, slot_begin, slot_end, theta2, wcounts, p2p, lshift, gorder, gcost);
   else
@@ -416,7 +477,7 @@ walk2_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, dou
 }
 
 // Heaviest-first launch order for the next walk (one CTA): gorder = the groups sorted by descending gcost, by a
-// counting sort on 1024 cost classes.  Every walk launch takes ~0.2 ms beyond its issue-slot work whatever the grid
+// counting sort on 1024 cost classes.  Every walk launch takes ~0.1-0.2 ms beyond its issue-slot work whatever the grid
 // (profiles/README.md): it ends with whatever its last CTAs happen to be, the groups differ by up to 2x in work (std
 // 18 % of the mean), and the hardware hands CTAs to the SMs in index order.  Dealing the heavy groups first shortens
 // that drain of the machine: measured 2.187 -> 2.107 ms at 31251 CTAs (N = 1M) and 0.370 -> 0.303 ms at the 3907 CTAs

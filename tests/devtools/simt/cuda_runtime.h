@@ -145,6 +145,20 @@ static inline T __shfl_down_sync(unsigned mask, T v, unsigned d) {
   const int l = simt::cur->lane;
   return l + (int)d < 32 ? simt::from_bits<T>(s[l + d]) : v;
 }
+static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) {
+  const uint64_t* s = simt::warp_exchange(mask, v);
+  unsigned r = 0xffffffffu;
+  for (int l = 0; l < 32; ++l)
+    if (((mask >> l) & 1u) && (unsigned)s[l] < r) r = (unsigned)s[l];
+  return r;
+}
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
+  const uint64_t* s = simt::warp_exchange(mask, v);
+  unsigned r = 0u;
+  for (int l = 0; l < 32; ++l)
+    if (((mask >> l) & 1u) && (unsigned)s[l] > r) r = (unsigned)s[l];
+  return r;
+}
 static inline unsigned __match_any_sync(unsigned mask, unsigned v) {
   const uint64_t* s = simt::warp_exchange(mask, v);
   unsigned r = 0;
@@ -301,6 +315,8 @@ static inline void cudaGraphSetConditional(cudaGraphConditionalHandle, unsigned)
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new simt_event(); return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+enum { cudaEventRecordDefault = 0, cudaEventRecordExternal = 1 };
+static inline cudaError_t cudaEventRecordWithFlags(cudaEvent_t e, cudaStream_t s, unsigned) { return cudaEventRecord(e, s); }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
   *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();

@@ -51,9 +51,48 @@ static void tl_flush_sparse(wm_stats* o, int c) {
   t->ns = 0;
 }
 static void sw_emit(wm_stats* o, uint32_t m);
+// ---- tile-drain model: the list (capacity TI_CAP[c]) is drained once per sub-group of g targets (g = 16, 8, 4) with
+// 32/g lanes per target, U interactions in flight per lane: a pass over a sub-group costs ceil(cnt_sub / (L*U)) * U
+// lane-iterations, cnt_sub = entries whose mask meets the sub-group.  ti[c][0] = today's iterations (ceil(cnt/4)*4),
+// ti[c][1..] = (g=16,U=4) (g=8,U=4) (g=8,U=2) (g=4,U=2) (g=4,U=1) (g=8,U=1) ; ti[c][7] = drains
+static const int TI_CAP[4] = {96, 128, 192, 256};
+double g_ti[4][8];
+typedef struct { int cnt; uint32_t m[256]; } ti_state;
+static ti_state g_tis[4];
+static int ti_pass(const ti_state* t, int g, int U) {
+  const int L = 32 / g; int tot = 0;
+  for (int sub = 0; sub < 32 / g; ++sub) {
+    const uint32_t sm = (g == 32 ? 0xffffffffu : ((1u << g) - 1u)) << (sub * g);
+    int c = 0;
+    for (int i = 0; i < t->cnt; ++i) c += (t->m[i] & sm) != 0;
+    tot += (c + L * U - 1) / (L * U) * U;
+  }
+  return tot;
+}
+static void ti_flush(int c) {
+  ti_state* t = &g_tis[c];
+  if (!t->cnt) return;
+  g_ti[c][0] += (t->cnt + 3) / 4 * 4;
+  g_ti[c][1] += ti_pass(t, 16, 4);
+  g_ti[c][2] += ti_pass(t, 8, 4);
+  g_ti[c][3] += ti_pass(t, 8, 2);
+  g_ti[c][4] += ti_pass(t, 4, 2);
+  g_ti[c][5] += ti_pass(t, 4, 1);
+  g_ti[c][6] += ti_pass(t, 8, 1);
+  g_ti[c][7] += 1;
+  t->cnt = 0;
+}
+static void ti_emit(uint32_t m) {
+  for (int c = 0; c < 4; ++c) {
+    if (g_tis[c].cnt == TI_CAP[c]) ti_flush(c);
+    g_tis[c].m[g_tis[c].cnt++] = m;
+  }
+}
+static void ti_end_group(void) { for (int c = 0; c < 4; ++c) ti_flush(c); }
 static void tl_emit(wm_stats* o, uint32_t m) {
   if (!m) return;
   sw_emit(o, m);
+  ti_emit(m);
   for (int c = 0; c < 8; ++c) {
     tl_state* t = &g_tl[c];
     if (popc(m) >= TL_T[c]) {
@@ -104,22 +143,31 @@ static void sw_end_group(wm_stats* o) {
 }
 
 // group = 32 consecutive tree slots starting at base; slot -> particle id through idx[]
+// optional explicit groups (wm_set_groups): group g = slots [gbase[g], gbase[g] + gcount[g]), gcount <= 32
+static const uint64_t* g_gbase; static const uint32_t* g_gcount;
+void wm_set_groups(const uint64_t* b, const uint32_t* c) { g_gbase = b; g_gcount = c; }
+// optional lane -> slot map per group (32 entries each, ~0 = empty lane); overrides base + lane
+static const uint64_t* g_lanes;
+void wm_set_lanes(const uint64_t* m) { g_lanes = m; }
+#define SLOT(g_, l_) (g_lanes ? g_lanes[(g_) * 32 + (l_)] : (base + (l_) < gend ? base + (l_) : ~0ull))
 void wm_run(const okd_node* nodes, const okd_particle* parts, const uint64_t* idx, uint64_t n, double theta,
             uint64_t first_group, uint64_t n_groups, uint64_t stride, int defer, int hard, wm_stats* out) {
   const double theta2 = theta * theta;
   memset(out, 0, sizeof(*out));
+  memset(g_ti, 0, sizeof(g_ti));
   enum { CAP = 4096 };
   uint32_t* snode = malloc(sizeof(uint32_t) * CAP);
   uint32_t* smask = malloc(sizeof(uint32_t) * CAP);
   uint32_t pn[CAP], pm[CAP], ln_[CAP], lm[CAP];
   for (uint64_t g = 0; g < n_groups; ++g) {
-    const uint64_t base = (first_group + g * stride) * 32;
+    const uint64_t base = g_gbase ? g_gbase[first_group + g * stride] : (first_group + g * stride) * 32;
+    const uint64_t gend = g_gbase ? base + g_gcount[first_group + g * stride] : n;
     if (base >= n) break;
     double px[32], py[32], pz[32], lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     uint32_t m0 = 0;
     for (int l = 0; l < 32; ++l) {
-      if (base + l >= n) continue;
-      const okd_particle* p = &parts[idx[base + l]];
+      if (SLOT(first_group + g * stride, l) == ~0ull) continue;
+      const okd_particle* p = &parts[idx[SLOT(first_group + g * stride, l)]];
       px[l] = p->p[0], py[l] = p->p[1], pz[l] = p->p[2];
       m0 |= 1u << l;
       for (int k = 0; k < 3; ++k) {
@@ -184,7 +232,7 @@ void wm_run(const okd_node* nodes, const okd_particle* parts, const uint64_t* id
               uint32_t m = mk;
               const uint64_t pid = q->u.leaf.leaf_parts[k];
               for (int l = 0; l < 32; ++l)
-                if (base + l < n && idx[base + l] == pid) m &= ~(1u << l);
+                if (SLOT(first_group + g * stride, l) != ~0ull && idx[SLOT(first_group + g * stride, l)] == pid) m &= ~(1u << l);
               adds++;
               out->entries++;
               out->part_entries++;
@@ -223,7 +271,7 @@ void wm_run(const okd_node* nodes, const okd_particle* parts, const uint64_t* id
               uint32_t m = mk;
               const uint64_t pid = q->u.leaf.leaf_parts[k];
               for (int l = 0; l < 32; ++l)
-                if (base + l < n && idx[base + l] == pid) m &= ~(1u << l);
+                if (SLOT(first_group + g * stride, l) != ~0ull && idx[SLOT(first_group + g * stride, l)] == pid) m &= ~(1u << l);
               out->entries++, out->part_entries++;
               out->lanes += popc(m);
               tl_emit(out, m);
@@ -287,6 +335,7 @@ void wm_run(const okd_node* nodes, const okd_particle* parts, const uint64_t* id
     }
     tl_end_group(out);
     sw_end_group(out);
+    ti_end_group();
   }
   free(snode);
   free(smask);

@@ -35,3 +35,7 @@ for defer, hard in ((0, 320), (1, 320)):
     for c in range(8):
         dn, sr = d[f"sw{2*c}"] / g, d[f"sw{2*c+1}"] / g
         print(f"   sliding window T={T[c]} W={W[c]}: dense iterations {dn:.0f}  rounds {sr:.0f}  (ideal {(d['lanes'] / g) / 32:.0f} at T=33)")
+    ti = (C.c_double * 32).in_dll(lib, "g_ti")
+    for c, cap in enumerate([96, 128, 192, 256]):
+        r = [ti[8 * c + k] / g for k in range(8)]
+        print(f"   tile drain cap={cap}: today {r[0]:.0f} | g16/U4 {r[1]:.0f}  g8/U4 {r[2]:.0f}  g8/U2 {r[3]:.0f}  g8/U1 {r[6]:.0f}  g4/U2 {r[4]:.0f}  g4/U1 {r[5]:.0f}  ({r[7]:.1f} drains)")
