@@ -693,8 +693,9 @@ int kdnb_download_accel(kdnb_ctx* ctx, double* acc) {
   NEED_PARTICLES(c);
   if (c->empty) return 0;
   if (!acc) return c->fail(KDNB_E_INVALID, "null output array");
-  if (!c->tree_valid) {
-    // before any build (or after a kick) the reference's acc vector is all zeros (:624-627, :659-661)
+  if (!c->tree_valid || !c->acc_valid) {
+    // before the first calc_accel and after every kick the reference's acc vector is all zeros (:624-627, :659-661);
+    // the device keeps that state as a flag (acc_valid), not as 24 bytes per particle of zeros
     memset(acc, 0, 3 * c->n * sizeof(double));
     return 0;
   }

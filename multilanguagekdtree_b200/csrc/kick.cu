@@ -30,11 +30,14 @@ static AccSel acc_sel(const Ctx* c) {
   return a;
 }
 
-// thread i = particle i (original order); its acceleration lives at tree slot rank[i].  The same thread zeroes that
-// acceleration (a[k] = 0, :659-661) and folds the new position into the extents the next build's sort scales its keys
-// to (accumulate_extent, common.cuh): the step has no separate pass over the positions.
+// thread i = particle i (original order); its acceleration lives at tree slot rank[i].  The same thread folds the new
+// position into the extents the next build's sort scales its keys to (accumulate_extent, common.cuh): the step has no
+// separate pass over the positions.  `a[k] = 0` (:659-661) costs no memory traffic: the context remembers that the
+// accelerations were consumed (acc_valid = false) — a kick without a walk in between then runs with use_acc = false
+// (a = 0, exactly what the reference's zeroed vector gives), and downloading them yields zeros.  (Measured: zeroing the
+// gathered 24 bytes in place doubles the kernel's time at N = 10M, a separate memset is a launch and 24 B / particle.)
 __global__ void __launch_bounds__(256) kick_drift_kernel(uint32_t n, double dt, V3 pos, V3 vel,
-                                                         const uint32_t* __restrict__ rank, AccSel sel,
+                                                         const uint32_t* __restrict__ rank, AccSel sel, bool use_acc,
                                                          PosM* __restrict__ pm, uint64_t* __restrict__ ss) {
   pdl_sync();
   __shared__ uint64_t sm[8][8];
@@ -44,20 +47,18 @@ __global__ void __launch_bounds__(256) kick_drift_kernel(uint32_t n, double dt, 
   if (valid) {
     // every load of the particle before its first store: the arrays are not provably disjoint for the compiler, so a
     // store in between would order the later loads behind it (five dependent round trips instead of two)
-    double* acc_t = acc_buf(sel);
+    const double* acc_t = acc_buf(sel);
     const uint64_t j = rank[i];
     const double u0 = vel.p[0][i], u1 = vel.p[1][i], u2 = vel.p[2][i];
     const double p0 = pos.p[0][i], p1 = pos.p[1][i], p2 = pos.p[2][i];
-    const double a0 = acc_t[3 * j + 0], a1 = acc_t[3 * j + 1], a2 = acc_t[3 * j + 2];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    if (use_acc) a0 = acc_t[3 * j + 0], a1 = acc_t[3 * j + 1], a2 = acc_t[3 * j + 2];
     const double v0 = __dadd_rn(u0, __dmul_rn(dt, a0));  // b.v[k] += dt * a[k]   (:650-652)
     const double v1 = __dadd_rn(u1, __dmul_rn(dt, a1));
     const double v2 = __dadd_rn(u2, __dmul_rn(dt, a2));
     x = __dadd_rn(p0, __dmul_rn(dt, v0));  // dx = dt*v; p += dx     (:653-658)
     y = __dadd_rn(p1, __dmul_rn(dt, v1));
     z = __dadd_rn(p2, __dmul_rn(dt, v2));
-    acc_t[3 * j + 0] = 0.0;  // a[k] = 0 (:659-661)
-    acc_t[3 * j + 1] = 0.0;
-    acc_t[3 * j + 2] = 0.0;
     vel.p[0][i] = v0;
     vel.p[1][i] = v1;
     vel.p[2][i] = v2;
@@ -74,9 +75,11 @@ __global__ void __launch_bounds__(256) kick_drift_kernel(uint32_t n, double dt, 
 int kick_drift(Ctx* c, double dt) {
   const uint32_t n = (uint32_t)c->n;
   V3 pos = {{c->pos[0], c->pos[1], c->pos[2]}}, vel = {{c->vel[0], c->vel[1], c->vel[2]}};
-  KDNB_LAUNCH(c, kick_drift_kernel, (n + 255) / 256, 256, 0, n, dt, pos, vel, c->rank, acc_sel(c), c->pm, c->sort_state);
+  KDNB_LAUNCH(c, kick_drift_kernel, (n + 255) / 256, 256, 0, n, dt, pos, vel, c->rank, acc_sel(c), c->acc_valid, c->pm,
+              c->sort_state);
   KDNB_CHECK_LAUNCH(c);
   c->extent_fresh = true;
+  c->acc_valid = false;   // a = 0: consumed
   c->tree_valid = false;  // positions moved: the tree no longer describes them
   return 0;
 }
