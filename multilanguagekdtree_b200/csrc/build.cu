@@ -249,10 +249,10 @@ struct __align__(4) BotTab {
 static_assert(sizeof(BotTab) == 12, "BotTab");
 
 #ifndef KDNB_BOT_THREADS
-#define KDNB_BOT_THREADS 512
+#define KDNB_BOT_THREADS 256
 #endif
 constexpr int BOT_THREADS = KDNB_BOT_THREADS;
-constexpr int BOT_IPT = BOT_CAP / BOT_THREADS;  // 4
+constexpr int BOT_IPT = BOT_CAP / BOT_THREADS;
 constexpr int BOT_WARPS = BOT_THREADS / 32;
 
 struct BotSmem {
@@ -277,7 +277,7 @@ static inline uint32_t bot_heap(uint32_t mp) {
 static inline size_t bot_smem_bytes(uint32_t mp) { return sizeof(BotSmem) + (bot_heap(mp) - 1) * sizeof(BotTab); }
 
 #ifndef KDNB_BOT_MINB
-#define KDNB_BOT_MINB 4
+#define KDNB_BOT_MINB 6
 #endif
 __global__ void __launch_bounds__(BOT_THREADS, KDNB_BOT_MINB)
 build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_t mp, int layout,

@@ -35,7 +35,8 @@ struct __align__(32) PosM {
 };
 
 #ifndef KDNB_BOT_CAP
-#define KDNB_BOT_CAP 2048  // (compile-time experiment knob: -DKDNB_BOT_CAP=1024 -DKDNB_BOT_THREADS=256, see build.py)
+#define KDNB_BOT_CAP 1024  // 1024 slots x 256 threads x 6 CTAs/SM: measured against 2048 x 512 x 4 (profiles/r02_ab_build_botcap.txt:
+                           // build 0.514 -> 0.487 ms at N=1M, 4.45 -> 3.96 ms at N=10M); compile-time knob with KDNB_BOT_THREADS / _MINB
 #endif
 constexpr int BOT_CAP = KDNB_BOT_CAP;  // largest segment handled entirely in shared memory by the bottom build kernel
 constexpr int MAX_LEVELS = 40;
