@@ -42,6 +42,19 @@ typedef struct kdnb_particle {
   double m;
 } kdnb_particle;
 
+/* mirrors the Sequential crate's SIMD particle, `pub struct Particle { p: f64x4, v: f64x4, r: f64, m: f64 }`
+ * (Sequential/RustVersion/src/simd_particle.rs:3-8): f64x4 is 32-byte aligned, so the record is 96 bytes.  Lane 3 of p
+ * and v is padding: the reference's own generators leave it 0 (simd_particle.rs:13-26, :30-52) and its arithmetic keeps
+ * it 0 (`(d * d).reduce_sum()`, simd_kd_tree.rs:151-152, adds an exact 0).  A non-zero lane 3 would be a fourth spatial
+ * dimension there; the kdnb_*_simd calls reject it (KDNB_E_INVALID at the next synchronising call). */
+typedef struct kdnb_particle_simd {
+  double p[4];
+  double v[4];
+  double r;
+  double m;
+  double pad_[2];
+} kdnb_particle_simd;
+
 enum { KDNB_LEAF = 0, KDNB_INTERNAL = 1 };
 #define KDNB_NO_INDEX UINT64_MAX /* usize::MAX of NEGS (array_kd_tree.rs:16) */
 
@@ -162,6 +175,13 @@ uint64_t kdnb_launch_count(const kdnb_ctx* ctx);     /* kernels launched by this
 int kdnb_measure_fp64_peak(kdnb_ctx* ctx, double* tflops_out); /* DFMA-chain microbenchmark: the walk's roofline denominator */
 int kdnb_flush_l2(kdnb_ctx* ctx);                     /* overwrite a 256 MiB scratch buffer */
 int kdnb_device_ms(kdnb_ctx* ctx, int begin_or_end, double* ms_out); /* CUDA-event stopwatch on the context's stream */
+
+/* ---- the Sequential crate's SIMD particle surface (simd_particle.rs / simd_kd_tree.rs:169-202): the same step on
+ * 96-byte f64x4 records; create the context with max_parts = 7 and KDNB_LAYOUT_DENSE for that crate's tree
+ * (simd_kd_tree.rs:9, :49-138).  Same arithmetic as the scalar record: the results are bit-identical. */
+int kdnb_upload_particles_simd(kdnb_ctx* ctx, const kdnb_particle_simd* aos, uint64_t count);
+int kdnb_download_particles_simd(kdnb_ctx* ctx, kdnb_particle_simd* out, uint64_t capacity);
+int kdnb_simple_sim_bodies_simd(kdnb_ctx* ctx, kdnb_particle_simd* bodies, uint64_t count, double dt, int64_t steps);
 
 /* page-locked host buffers for the transfers above (optional; any host pointer works, pinned is faster) */
 void* kdnb_host_alloc(uint64_t bytes);

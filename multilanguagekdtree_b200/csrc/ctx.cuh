@@ -54,6 +54,8 @@ struct Ctx {
   double* mass = nullptr;
   double* radius = nullptr;
   kdnb_particle* aos = nullptr;  // staging for AoS <-> SoA conversion
+  kdnb_particle_simd* aos_simd = nullptr;  // staging of the 96-byte SIMD records (allocated by the first kdnb_*_simd call)
+  uint64_t aos_simd_cap = 0;
   PosM* pm = nullptr;            // {x, y, z, m} in original order: one-sector gathers for the bottom build kernel
 
   // build scratch
@@ -135,6 +137,8 @@ int walk(Ctx* c);
 int kick_drift(Ctx* c, double dt);
 int p2p_wait_step(Ctx* c);
 int aos_to_soa(Ctx* c);
+int simd_to_soa(Ctx* c, const kdnb_particle_simd* dev_aos);
+int soa_to_simd(Ctx* c, kdnb_particle_simd* dev_aos);
 int soa_to_aos(Ctx* c);
 int gather_acc(Ctx* c, double* dst_orig_order);
 int scatter_acc(Ctx* c, const double* src_orig_order);

@@ -98,6 +98,8 @@ static void free_all(Ctx* c) {
   fr(c->mass);
   fr(c->radius);
   fr(c->aos);
+  fr(c->aos_simd);
+  c->aos_simd_cap = 0;
   fr(c->keys[0]);
   fr(c->keys[1]);
   fr(c->list[0]);
@@ -664,6 +666,58 @@ int kdnb_simple_sim_bodies(kdnb_ctx* ctx, kdnb_particle* bodies, uint64_t count,
   if (int rc = kdnb_upload_particles(ctx, bodies, count)) return rc;
   if (int rc = kdnb_simple_sim(ctx, dt, steps)) return rc;
   return kdnb_download_particles(ctx, bodies, count);
+}
+
+// ---- the Sequential crate's SIMD particle surface (simd_particle.rs:3-8, simd_kd_tree.rs:169-202)
+static int simd_staging(Ctx* c, uint64_t count) {
+  if (c->aos_simd && c->aos_simd_cap >= count) return 0;
+  if (int rc = dev_alloc(c, &c->aos_simd, count)) return rc;
+  c->aos_simd_cap = count;
+  return 0;
+}
+
+// a record whose padding lane was not 0 was uploaded (flag raised by simd_to_soa_kernel)
+static int check_simd_lanes(Ctx* c) {
+  if (!c->lvl_ctl) return 0;
+  uint32_t bad = 0;
+  KDNB_CUDA_TRY(c, cudaMemcpyAsync(&bad, c->lvl_ctl + 66, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
+  KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (bad) {
+    KDNB_CUDA_TRY(c, cudaMemsetAsync(c->lvl_ctl + 66, 0, sizeof(uint32_t), c->stream));
+    return c->fail(KDNB_E_INVALID, "kdnb_particle_simd: lane 3 of p / v must be 0 (it is padding in the reference's SIMD particle)");
+  }
+  return 0;
+}
+
+int kdnb_upload_particles_simd(kdnb_ctx* ctx, const kdnb_particle_simd* aos, uint64_t count) {
+  CTX_OR_FAIL(ctx);
+  if (count == 0) return upload_empty(c);
+  if (!aos) return c->fail(KDNB_E_INVALID, "null particle array");
+  if (int rc = plan(c, count)) return rc;
+  if (int rc = simd_staging(c, count)) return rc;
+  KDNB_CUDA_TRY(c, cudaMemcpyAsync(c->aos_simd, aos, count * sizeof(kdnb_particle_simd), cudaMemcpyHostToDevice, c->stream));
+  return simd_to_soa(c, c->aos_simd);
+}
+
+int kdnb_download_particles_simd(kdnb_ctx* ctx, kdnb_particle_simd* out, uint64_t capacity) {
+  CTX_OR_FAIL(ctx);
+  NEED_PARTICLES(c);
+  if (c->empty) return 0;
+  if (!out) return c->fail(KDNB_E_INVALID, "null output array");
+  if (capacity < c->n) return c->fail(KDNB_E_CAPACITY, "output array smaller than the particle count");
+  if (int rc = simd_staging(c, c->n)) return rc;
+  if (int rc = soa_to_simd(c, c->aos_simd)) return rc;
+  KDNB_CUDA_TRY(c, cudaMemcpyAsync(out, c->aos_simd, c->n * sizeof(kdnb_particle_simd), cudaMemcpyDeviceToHost, c->stream));
+  KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (int rc = check_simd_lanes(c)) return rc;
+  return check_peer_timeout(c);
+}
+
+int kdnb_simple_sim_bodies_simd(kdnb_ctx* ctx, kdnb_particle_simd* bodies, uint64_t count, double dt, int64_t steps) {
+  if (int rc = kdnb_upload_particles_simd(ctx, bodies, count)) return rc;
+  if (int rc = check_simd_lanes(&ctx->c)) return rc;  // before the caller's records are overwritten
+  if (int rc = kdnb_simple_sim(ctx, dt, steps)) return rc;
+  return kdnb_download_particles_simd(ctx, bodies, count);
 }
 
 int kdnb_simple_sim_host(const kdnb_config* cfg, kdnb_particle* bodies, uint64_t count, double dt, int64_t steps) {

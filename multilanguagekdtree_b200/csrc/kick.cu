@@ -138,6 +138,73 @@ __global__ void __launch_bounds__(256) soa_to_aos_kernel(uint32_t n, kdnb_partic
   q[3] = make_double2(radius[i], mass[i]);
 }
 
+// the Sequential crate's SIMD particle (simd_particle.rs:3-8): 96-byte records {p[4], v[4], r, m, pad}.  Lane 3 is
+// padding in the reference (always 0); a record with a non-zero lane 3 raises the context's input-error flag.
+__global__ void __launch_bounds__(256) simd_to_soa_kernel(uint32_t n, const kdnb_particle_simd* __restrict__ aos, V3 pos,
+                                                          V3 vel, double* __restrict__ radius,
+                                                          double* __restrict__ mass, PosM* __restrict__ pm,
+                                                          uint64_t* __restrict__ ss, uint32_t* __restrict__ bad) {
+  pdl_sync();
+  __shared__ uint64_t sm[8][8];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  double x = 0.0, y = 0.0, z = 0.0;
+  uint32_t light = 0u;
+  if (valid) {
+    const double2* q = reinterpret_cast<const double2*>(aos + i);
+    const double2 p01 = q[0], p23 = q[1], v01 = q[2], v23 = q[3], rm = q[4];
+    if (p23.y != 0.0 || v23.y != 0.0) *bad = 1u;  // (also NaN: not a padding lane)
+    x = p01.x, y = p01.y, z = p23.x;
+    pos.p[0][i] = x;
+    pos.p[1][i] = y;
+    pos.p[2][i] = z;
+    vel.p[0][i] = v01.x;
+    vel.p[1][i] = v01.y;
+    vel.p[2][i] = v23.x;
+    radius[i] = rm.x;
+    mass[i] = rm.y;
+    PosM rec;
+    rec.x = x, rec.y = y, rec.z = z, rec.m = rm.y;
+    pm[i] = rec;
+    light = (rm.y > 0.0) ? 0u : 1u;
+  }
+  accumulate_extent(x, y, z, valid, light, ss, sm);
+}
+
+__global__ void __launch_bounds__(256) soa_to_simd_kernel(uint32_t n, kdnb_particle_simd* __restrict__ aos, V3 pos, V3 vel,
+                                                          const double* __restrict__ radius,
+                                                          const double* __restrict__ mass) {
+  pdl_sync();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double2* q = reinterpret_cast<double2*>(aos + i);
+  q[0] = make_double2(pos.p[0][i], pos.p[1][i]);
+  q[1] = make_double2(pos.p[2][i], 0.0);  // lane 3 stays 0: v[3] += dt * 0, p[3] += dt * v[3] (simd_kd_tree.rs:195-198)
+  q[2] = make_double2(vel.p[0][i], vel.p[1][i]);
+  q[3] = make_double2(vel.p[2][i], 0.0);
+  q[4] = make_double2(radius[i], mass[i]);
+  q[5] = make_double2(0.0, 0.0);
+}
+
+int simd_to_soa(Ctx* c, const kdnb_particle_simd* dev_aos) {
+  const uint32_t n = (uint32_t)c->n;
+  V3 pos = {{c->pos[0], c->pos[1], c->pos[2]}}, vel = {{c->vel[0], c->vel[1], c->vel[2]}};
+  KDNB_LAUNCH(c, extent_reset_kernel, 1, EXT_PARTS, 0, c->sort_state);
+  KDNB_LAUNCH(c, simd_to_soa_kernel, (n + 255) / 256, 256, 0, n, dev_aos, pos, vel, c->radius, c->mass, c->pm,
+              c->sort_state, c->lvl_ctl + 66);
+  KDNB_CHECK_LAUNCH(c);
+  c->extent_fresh = true;
+  return 0;
+}
+
+int soa_to_simd(Ctx* c, kdnb_particle_simd* dev_aos) {
+  const uint32_t n = (uint32_t)c->n;
+  V3 pos = {{c->pos[0], c->pos[1], c->pos[2]}}, vel = {{c->vel[0], c->vel[1], c->vel[2]}};
+  KDNB_LAUNCH(c, soa_to_simd_kernel, (n + 255) / 256, 256, 0, n, dev_aos, pos, vel, c->radius, c->mass);
+  KDNB_CHECK_LAUNCH(c);
+  return 0;
+}
+
 int aos_to_soa(Ctx* c) {
   const uint32_t n = (uint32_t)c->n;
   V3 pos = {{c->pos[0], c->pos[1], c->pos[2]}}, vel = {{c->vel[0], c->vel[1], c->vel[2]}};

@@ -13,6 +13,17 @@ pub struct kdnb_particle {
     pub m: c_double,
 }
 
+/// `#[repr(C)]` twin of the Sequential crate's SIMD particle, `Particle { p: f64x4, v: f64x4, r, m }`
+/// (Sequential/RustVersion/src/simd_particle.rs:3-8): f64x4 is 32-byte aligned, 96 bytes; lane 3 of p / v is padding (0).
+#[repr(C, align(32))]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct kdnb_particle_simd {
+    pub p: [c_double; 4],
+    pub v: [c_double; 4],
+    pub r: c_double,
+    pub m: c_double,
+}
+
 pub const KDNB_LEAF: u32 = 0;
 pub const KDNB_INTERNAL: u32 = 1;
 pub const KDNB_NO_INDEX: u64 = u64::MAX;
@@ -91,6 +102,9 @@ extern "C" {
     pub fn kdnb_measure_fp64_peak(ctx: *mut kdnb_ctx, tflops_out: *mut c_double) -> c_int;
     pub fn kdnb_flush_l2(ctx: *mut kdnb_ctx) -> c_int;
     pub fn kdnb_device_ms(ctx: *mut kdnb_ctx, begin_or_end: c_int, ms_out: *mut c_double) -> c_int;
+    pub fn kdnb_upload_particles_simd(ctx: *mut kdnb_ctx, aos: *const kdnb_particle_simd, count: u64) -> c_int;
+    pub fn kdnb_download_particles_simd(ctx: *mut kdnb_ctx, out: *mut kdnb_particle_simd, capacity: u64) -> c_int;
+    pub fn kdnb_simple_sim_bodies_simd(ctx: *mut kdnb_ctx, bodies: *mut kdnb_particle_simd, count: u64, dt: c_double, steps: i64) -> c_int;
     pub fn kdnb_host_alloc(bytes: u64) -> *mut c_void;
     pub fn kdnb_host_free(p: *mut c_void);
 }

@@ -14,6 +14,12 @@ seeded circular_orbits (the reference's are unseeded) and are stored in the fixt
 PureVersion follows the same operation order as the Rust code (sequential node sums, pairwise walk,
 kick then drift), so the oracle's dense + faithful mode must reproduce these files BIT FOR BIT
 (tests/test_oracle_golden.py).
+
+One case (`pure3d_*`) needs ONE documented source patch: PureVersion never considers z as a split dimension
+(`for dim in range(1, 2):  # FIXME: what is this`, kd_tree.py:96), while the Rust hot path loops over all three
+(`for dim in 1..3`, Parallel/RustVersion/src/array_kd_tree.rs:552).  For that case the module is loaded from its
+source text with exactly that one token changed (`range(1, 2)` -> `range(1, 3)`), nothing else; the initial conditions
+get a z extent so that z IS chosen in many nodes.  It pins the 3-D split choice outside the oracle's own restatement.
 """
 from __future__ import annotations
 
@@ -92,7 +98,20 @@ def dump_tree(nodes, last: int, cap: int) -> dict:
     return d
 
 
-def case(name: str, parts0: np.ndarray, max_parts: int, pivot_seed: int, steps: int, dt: float):
+def load_3d_variant():
+    """kd_tree.py with the split-dimension loop over all three dimensions (the only change, see the module docstring)."""
+    import types
+    src = open(os.path.join(REF_SRC, "kd_tree.py")).read()
+    old = "for dim in range(1, 2):"
+    assert src.count(old) == 1, "reference source changed: re-check the patch"
+    mod = types.ModuleType("kd_tree_3d")
+    mod.__file__ = os.path.join(REF_SRC, "kd_tree.py")
+    sys.modules[mod.__name__] = mod  # (dataclasses look their module up by name)
+    exec(compile(src.replace(old, "for dim in range(1, 3):"), mod.__file__, "exec"), mod.__dict__)
+    return mod
+
+
+def case(name: str, parts0: np.ndarray, max_parts: int, pivot_seed: int, steps: int, dt: float, ref_kd=ref_kd):
     ref_kd.MAX_PARTS = max_parts
     rng = SplitMix64(pivot_seed)
     ref_kd.randrange = rng.randrange
@@ -129,6 +148,12 @@ def main():
     case("pure_ring11_mp8", orc.circular_orbits(11, seed=3), 8, 3003, 4, 1e-3)
     # two_bodies half orbit (Parallel/GoVersion/kdtree_test.go:63-74 prints this; no assertion there)
     case("pure_two_bodies", orc.two_bodies(), 8, 4004, 1000, math.pi / 1000)
+    # 3-D: the ring lifted out of its plane (z extent 4 against 10 in x / y, vertical velocities), all three split dimensions
+    p3 = orc.circular_orbits(400, seed=19)
+    i = np.arange(1, len(p3), dtype=np.float64)
+    p3["p"][1:, 2] = 2.0 * np.cos(1.7 * i)
+    p3["v"][1:, 2] = 0.05 * np.sin(0.3 * i)
+    case("pure3d_ring400_mp8", p3, 8, 5005, 4, 1e-3, ref_kd=load_3d_variant())
 
 
 if __name__ == "__main__":

@@ -396,16 +396,53 @@ def test_two_bodies_orbit(orc):
     assert abs(g["p"][1][0] + 1.0) < 2e-2
 
 
-def test_golden_reference_python_trajectory():
-    """The reference's own PureVersion output (tests/golden): 301 particles, 5 steps."""
+@pytest.mark.parametrize("name", ["pure_ring300_mp8", "pure3d_ring400_mp8"])
+def test_golden_reference_python_trajectory(name):
+    """The reference's own PureVersion output (tests/golden): accelerations and a few steps; the 3-D case (z chosen as
+    split dimension in many nodes, see tests/golden/make_golden.py) also pins the dense tree's split planes bit for bit."""
     import os
-    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "pure_ring300_mp8.npz"))
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
     parts = gold["parts0"].view(PARTICLE).reshape(-1).copy()
     acc = kd.calc_accel_all(parts)
     assert rel_err(acc, gold["acc"]).max() <= ACC_RTOL
+    # build_tree (dense layout) against the reference's own nodes: topology and split planes are order-independent
+    nodes = kd.allocate_node_vec(len(parts))
+    idx = np.arange(len(parts), dtype=np.uint64)
+    last, nodes = kd.build_tree(idx, 0, len(parts), parts, 0, nodes)
+    assert last == int(gold["last"])
+    internal = gold["tree_is_internal"].astype(bool)
+    t = nodes[: last + 1]
+    assert np.array_equal(t["kind"] == kd.INTERNAL, internal)
+    for f in ("split_dim", "left", "right"):
+        assert np.array_equal(t[f][internal].astype(np.uint64), gold["tree_" + f][internal]), f
+    for f in ("split_val", "size"):
+        assert np.array_equal(t[f][internal].view(np.uint64), gold["tree_" + f][internal].view(np.uint64)), f
     kd.simple_sim(parts, float(gold["dt"]), int(gold["steps"]))
     after = gold["after"].view(PARTICLE).reshape(-1)
     assert np.abs(parts["p"] - after["p"]).max() / np.abs(after["p"]).max() <= POS_RTOL
+
+
+def test_simd_particle_surface_equals_scalar_path():
+    """Sequential crate, SIMD variant (simd_particle.rs:3-8, simd_kd_tree.rs:169-202): 96-byte f64x4 records through
+    kdnb_*_simd give bit for bit what the scalar records give with the same constants (MAX_PARTS=7, dense layout);
+    lane 3 comes back 0; a non-zero lane 3 is rejected."""
+    from multilanguagekdtree_b200 import simd_kd_tree, simd_particle
+    b = simd_particle.circular_orbits(3000, seed=5)
+    b["p"][1:, 2] = 0.01 * np.sin(np.arange(1, len(b)))      # some z extent: all three lanes carry data
+    s = simd_particle.to_scalar(b)
+    simd_kd_tree.simple_sim(b, 1e-3, 4)
+    kd.simple_sim(s, 1e-3, 4, max_parts=7)                   # scalar records, same constants (padded layout: same physics)
+    assert np.array_equal(b["p"][:, :3].view(np.uint64), s["p"].view(np.uint64))
+    assert np.array_equal(b["v"][:, :3].view(np.uint64), s["v"].view(np.uint64))
+    assert not b["p"][:, 3].any() and not b["v"][:, 3].any()
+    assert np.array_equal(b["m"], s["m"]) and np.array_equal(b["r"], s["r"])
+    two = simd_particle.two_bodies()
+    simd_kd_tree.simple_sim(two, np.pi / 1000, 1000)
+    assert abs(two["p"][1][0] + 1.0) < 2e-2                  # half an orbit
+    bad = simd_particle.circular_orbits(100, seed=1)
+    bad["v"][7, 3] = 1e-3
+    with pytest.raises(kd.KdnbError, match="lane 3"):
+        simd_kd_tree.simple_sim(bad, 1e-3, 1)
 
 
 def test_reference_api_mirror(orc):
