@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(LVL_THREADS, MINB)
 level_partition(Pos3c pos, Lists L, int level, uint32_t cps, uint32_t mp, int layout, uint4* __restrict__ tseg,
                 WNode* __restrict__ nodes, const uint32_t* __restrict__ rk, uint32_t n,
                 unsigned long long* __restrict__ status, uint32_t* __restrict__ lvl_ctl,
-                const uint32_t* __restrict__ flat) {
+                const uint32_t* __restrict__ flat, uint32_t seg_first) {
   pdl_sync();
   constexpr int IPT = LVL_CHUNK / LVL_THREADS;  // 8
   __shared__ uint32_t wtot[LVL_THREADS / 32];
@@ -151,7 +151,7 @@ level_partition(Pos3c pos, Lists L, int level, uint32_t cps, uint32_t mp, int la
   if (threadIdx.x == 0) s_ticket = atomicAdd(&lvl_ctl[level], 1u);
   __syncthreads();
   const uint32_t nseg = 1u << level;
-  const uint32_t seg = s_ticket / cps, chunk = s_ticket % cps;
+  const uint32_t seg = seg_first + s_ticket / cps, chunk = s_ticket % cps;  // (seg_first > 0: this rank's subtree only)
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
   if (threadIdx.x == 0) st = seg_stats(pos, L, level, seg, mp, layout, tseg, nodes, flat, rk, n, chunk == 0);
@@ -283,14 +283,14 @@ __global__ void __launch_bounds__(BOT_THREADS, KDNB_BOT_MINB)
 build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_t mp, int layout,
              const uint4* __restrict__ tseg, uint32_t* __restrict__ inv, WNode* __restrict__ nodes,
              double4* __restrict__ ms, uint32_t* __restrict__ perm, uint32_t* __restrict__ rank,
-             PosM* __restrict__ posm, const uint32_t* __restrict__ flat, uint32_t heap) {
+             PosM* __restrict__ posm, const uint32_t* __restrict__ flat, uint32_t heap, uint32_t seg_first) {
   pdl_sync();
   KDNB_DYN_SMEM(smem_raw);
   BotSmem& S = *reinterpret_cast<BotSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t lt = (1u << lane) - 1u;
   const uint32_t off = (1u << level) - 1;
-  const uint4 tb = tseg[off + blockIdx.x];
+  const uint4 tb = tseg[off + seg_first + blockIdx.x];
   const uint32_t a0 = tb.x, len0 = tb.y, node0 = tb.z;
   const uint32_t* const lx = L.l[tb.w & 1u][0];  // the buffer each list of this segment ended up in
   const uint32_t* const ly = L.l[(tb.w >> 1) & 1u][1];
@@ -527,13 +527,18 @@ build_bottom(Pos3c pos, const PosM* __restrict__ pm, Lists L, int level, uint32_
   }
 }
 
-// m / cm for the global levels (single CTA; at most a few thousand nodes)
-__global__ void __launch_bounds__(1024) build_topup(int l0, const uint4* __restrict__ tseg,
-                                                    WNode* __restrict__ nodes, double4* __restrict__ ms) {
+// m / cm for the global levels lev_hi-1 .. lev_lo (single CTA; at most a few thousand nodes).  Sharded builds run it
+// twice: first over the levels below the shard level for this rank's subtree only (seg_shift = level of the shard,
+// rank = its segment there), then — once every subtree root's sums have arrived — over the replicated top levels.
+__global__ void __launch_bounds__(1024) build_topup(int lev_hi, int lev_lo, int shard_level, uint32_t shard_seg,
+                                                    const uint4* __restrict__ tseg, WNode* __restrict__ nodes,
+                                                    double4* __restrict__ ms) {
   pdl_sync();
-  for (int lev = l0 - 1; lev >= 0; --lev) {
-    const uint32_t nn = 1u << lev, off = nn - 1;
-    for (uint32_t s = threadIdx.x; s < nn; s += blockDim.x) {
+  for (int lev = lev_hi - 1; lev >= lev_lo; --lev) {
+    uint32_t nn = 1u << lev, first = 0;
+    const uint32_t off = nn - 1;
+    if (shard_level >= 0) nn = 1u << (lev - shard_level), first = shard_seg << (lev - shard_level);
+    for (uint32_t s = first + threadIdx.x; s < first + nn; s += blockDim.x) {
       const uint32_t node = tseg[off + s].z;
       WNode* nd = &nodes[node];
       const double4 l = ms[node + 1], r = ms[nd->a];
@@ -546,6 +551,85 @@ __global__ void __launch_bounds__(1024) build_topup(int l0, const uint4* __restr
     }
     __syncthreads();
   }
+}
+
+// ------------------------------------------------------------------------------------------ sharded build: exchange
+// Rank r has built the subtree of level-k segment r: node records [node_first, node_first + node_cnt) (a subtree is a
+// contiguous index range in both layouts), tree slots [slot_first, slot_first + slot_cnt) of perm, and the root's mass
+// sums.  Every thread loads a piece once and stores it into every peer's copy over NVLink; a system-scope fence and the
+// last CTA then raise this rank's build flag on every peer (the same protocol as the accelerations, walk2.cuh).
+__global__ void __launch_bounds__(256) subtree_push_kernel(P2PBuild pb, uint64_t node_first, uint64_t node_cnt,
+                                                           uint32_t slot_first, uint32_t slot_cnt) {
+  pdl_sync();
+  const int me = pb.rank;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(pb.nodes[me] + node_first);
+    const uint64_t units = node_cnt * (sizeof(WNode) / sizeof(uint4));
+    for (uint64_t i = tid; i < units; i += nthr) {
+      const uint4 v = src[i];
+      for (int p = 0; p < pb.world; ++p)
+        if (p != me) reinterpret_cast<uint4*>(pb.nodes[p] + node_first)[i] = v;
+    }
+  }
+  {
+    const uint32_t* src = pb.perm[me] + slot_first;
+    for (uint64_t i = tid; i < slot_cnt; i += nthr) {
+      const uint32_t v = src[i];
+      for (int p = 0; p < pb.world; ++p)
+        if (p != me) pb.perm[p][slot_first + i] = v;
+    }
+  }
+  if (tid == 0) {
+    const double4 v = pb.ms[me][node_first];
+    for (int p = 0; p < pb.world; ++p)
+      if (p != me) pb.ms[p][node_first] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t* st = pb.state[me];
+    const uint32_t done = atomicAdd(&st[P2P_BDONE], 1u);
+    if (done == gridDim.x - 1) {
+      st[P2P_BDONE] = 0;
+      __threadfence_system();
+      const uint32_t epoch = st[P2P_BEPOCH];
+      for (int p = 0; p < pb.world; ++p) *reinterpret_cast<volatile uint32_t*>(pb.state[p] + P2P_BFLAGS + me) = epoch + 1u;
+    }
+  }
+}
+
+// one CTA per GPU: wait until every rank (this one included) has published its subtree of the current build
+__global__ void subtree_wait_kernel(uint32_t* state, int world) {
+  pdl_sync();
+  const uint32_t target = state[P2P_BEPOCH] + 1u;
+  volatile uint32_t* flags = state + P2P_BFLAGS;
+  if ((int)threadIdx.x < world) {
+    const long long t0 = clock64();
+    while (flags[threadIdx.x] < target) {
+      if (clock64() - t0 > (30LL << 30)) {  // ~15 s: a peer died; record it instead of hanging for ever
+        state[2] = 1u;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  if (threadIdx.x == 0) state[P2P_BEPOCH] = target;
+}
+
+// the tree-ordered particle copies and the id -> slot map of the slots OTHER ranks built: both follow from perm and the
+// (replicated) particle state, so they are gathered here instead of travelling over NVLink (32 + 4 bytes per particle)
+__global__ void __launch_bounds__(256) finish_foreign_kernel(uint32_t n, uint32_t own_first, uint32_t own_cnt,
+                                                             const uint32_t* __restrict__ perm,
+                                                             const PosM* __restrict__ pm, PosM* __restrict__ posm,
+                                                             uint32_t* __restrict__ rank) {
+  pdl_sync();
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n || (s - own_first) < own_cnt) return;
+  const uint32_t id = perm[s];
+  posm[s] = pm[id];
+  rank[id] = s;
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -565,6 +649,43 @@ __global__ void fill_unused(WNode* nodes, uint64_t count) {
 void init_unused_nodes(Ctx* c) {
   if (c->n_nodes == 0) return;
   KDNB_LAUNCH(c, fill_unused, (unsigned)((c->n_nodes + 255) / 256), 256, 0, c->nodes, c->n_nodes);
+}
+
+// level-k segment `seg` of the tree over n particles: first slot, length and node index (splits are always at len / 2,
+// :560, and a left subtree occupies the node indices right after its parent, :566-581 / :120-126), host side
+static void subtree_of(uint64_t n, uint32_t mp, int layout, int k, uint32_t seg, uint64_t* a, uint64_t* len, uint64_t* node) {
+  uint64_t fa = 0, fl = n, fn = 0;
+  for (int lev = k - 1; lev >= 0; --lev) {
+    const uint64_t left = fl / 2;
+    if ((seg >> lev) & 1u) {
+      fn += 1 + subtree_nodes(left, mp, layout);
+      fa += left;
+      fl -= left;
+    } else {
+      fn += 1;
+      fl = left;
+    }
+  }
+  *a = fa, *len = fl, *node = fn;
+}
+
+// Sharded build (this step): peer mode, world = 2^k, enough global levels, and a particle count where the exchange
+// (about 31 bytes per particle sent to every peer, four more launches) costs less than the part of the lower levels it
+// saves.  Measured (profiles/r02_ab_shard_build.txt): build 3.98 -> 3.19 ms at N=10M on 8 GPUs (step 7.12 -> 6.34 ms),
+// 0.504 -> 0.468 ms at N=1M on 8 GPUs, 0.497 -> 0.459 / 3.98 -> 3.50 ms at N=1M / 10M on 2 GPUs; every rank's tree stays
+// bit-identical to the single-GPU build (tests/multigpu_check.py).  KDNB_SHARD_BUILD=0 disables, =1 forces it wherever
+// it is possible.
+static int shard_level(const Ctx* c) {
+  static const int mode = [] {
+    const char* e = getenv("KDNB_SHARD_BUILD");
+    return e ? (atoi(e) != 0 ? 1 : 0) : -1;
+  }();
+  if (mode == 0 || c->world <= 1 || !c->p2p_on) return 0;
+  int k = 0;
+  while ((1 << k) < c->world) ++k;
+  if ((1 << k) != c->world || k > c->l0) return 0;
+  if (mode < 0 && c->n < 500000ull) return 0;
+  return k;
 }
 
 int build_tree(Ctx* c) {
@@ -587,20 +708,41 @@ int build_tree(Ctx* c) {
     return e ? atoi(e) : 0;
   }();
   const int lvl_minb = lvl_minb_env ? lvl_minb_env : ((c->n + LVL_CHUNK - 1) / LVL_CHUNK > 8ull * c->num_sms ? 8 : 4);
+  // multi-GPU: below level k every rank continues with the subtree of its own level-k segment only
+  const int k = shard_level(c);
+  c->shard_k = k;
+  const uint32_t me = (uint32_t)c->rank_id;
   for (int lev = 0; lev < c->l0; ++lev) {
-    const uint32_t nseg = 1u << lev;
-    const uint32_t maxlen = (uint32_t)((c->n + nseg - 1) >> lev);
+    const bool own = k > 0 && lev >= k;
+    const uint32_t nseg = own ? 1u << (lev - k) : 1u << lev;
+    const uint32_t seg_first = own ? me << (lev - k) : 0u;
+    const uint32_t maxlen = (uint32_t)((c->n + (1ull << lev) - 1) >> lev);
     const uint32_t cps = (maxlen + LVL_CHUNK - 1) / LVL_CHUNK;
 #define KDNB_LVL_ARGS pos, L, lev, cps, c->mp, c->layout, c->tseg, c->nodes, c->rk, n, \
-                      reinterpret_cast<unsigned long long*>(c->lvl_status), c->lvl_ctl, c->flat
+                      reinterpret_cast<unsigned long long*>(c->lvl_status), c->lvl_ctl, c->flat, seg_first
     if (lvl_minb == 8) KDNB_LAUNCH(c, (level_partition<8>), nseg * cps, LVL_THREADS, 0, KDNB_LVL_ARGS);
     else if (lvl_minb == 6) KDNB_LAUNCH(c, (level_partition<6>), nseg * cps, LVL_THREADS, 0, KDNB_LVL_ARGS);
     else KDNB_LAUNCH(c, (level_partition<4>), nseg * cps, LVL_THREADS, 0, KDNB_LVL_ARGS);
 #undef KDNB_LVL_ARGS
   }
-  KDNB_LAUNCH(c, build_bottom, 1u << c->l0, BOT_THREADS, bot_smem_bytes(c->mp), pos, c->pm, L, c->l0, c->mp, c->layout,
-              c->tseg, c->inv, c->nodes, c->ms, c->perm, c->rank, c->posm, c->flat, bot_heap(c->mp));
-  if (c->l0 > 0) KDNB_LAUNCH(c, build_topup, 1, 1024, 0, c->l0, c->tseg, c->nodes, c->ms);
+  if (k == 0) {
+    KDNB_LAUNCH(c, build_bottom, 1u << c->l0, BOT_THREADS, bot_smem_bytes(c->mp), pos, c->pm, L, c->l0, c->mp, c->layout,
+                c->tseg, c->inv, c->nodes, c->ms, c->perm, c->rank, c->posm, c->flat, bot_heap(c->mp), 0u);
+    if (c->l0 > 0) KDNB_LAUNCH(c, build_topup, 1, 1024, 0, c->l0, 0, -1, 0u, c->tseg, c->nodes, c->ms);
+  } else {
+    KDNB_LAUNCH(c, build_bottom, 1u << (c->l0 - k), BOT_THREADS, bot_smem_bytes(c->mp), pos, c->pm, L, c->l0, c->mp,
+                c->layout, c->tseg, c->inv, c->nodes, c->ms, c->perm, c->rank, c->posm, c->flat, bot_heap(c->mp),
+                me << (c->l0 - k));
+    if (c->l0 > k) KDNB_LAUNCH(c, build_topup, 1, 1024, 0, c->l0, k, k, me, c->tseg, c->nodes, c->ms);
+    uint64_t a = 0, len = 0, node = 0;
+    subtree_of(c->n, c->mp, c->layout, k, me, &a, &len, &node);
+    const uint64_t cnt = subtree_nodes(len, c->mp, c->layout);
+    KDNB_LAUNCH(c, subtree_push_kernel, 4 * c->num_sms, 256, 0, c->p2pb, node, cnt, (uint32_t)a, (uint32_t)len);
+    KDNB_LAUNCH(c, subtree_wait_kernel, 1, 32, 0, c->p2p_state, c->world);
+    KDNB_LAUNCH(c, finish_foreign_kernel, (n + 255) / 256, 256, 0, n, (uint32_t)a, (uint32_t)len, c->perm, c->pm, c->posm,
+                c->rank);
+    KDNB_LAUNCH(c, build_topup, 1, 1024, 0, k, 0, -1, 0u, c->tseg, c->nodes, c->ms);
+  }
   KDNB_CHECK_LAUNCH(c);
   c->tree_valid = true;
   c->map_valid = true;

@@ -28,6 +28,20 @@ struct P2P {
   int world, rank;
 };
 
+// Sharded tree build (multi-GPU, peer mode, world = 2^k): the top k levels are built by every rank, below them rank r
+// builds only the subtree of level-k segment r and stores its node records, its slice of the tree order (perm) and its
+// root's mass sums straight into every peer's buffers; a flag per rank publishes them (build.cu).
+// p2p_state words: [0] acc epoch, [1] acc cta_done, [2] error, [4..20) acc flags, [20..36) build flags, [36] build epoch,
+// [37] build cta_done
+constexpr int P2P_BFLAGS = 4 + P2P_MAX, P2P_BEPOCH = 4 + 2 * P2P_MAX, P2P_BDONE = 5 + 2 * P2P_MAX, P2P_WORDS = 8 + 2 * P2P_MAX;
+struct P2PBuild {
+  WNode* nodes[P2P_MAX];     // peers' node arrays, own included
+  uint32_t* perm[P2P_MAX];   // peers' tree order
+  double4* ms[P2P_MAX];      // peers' per-node mass sums
+  uint32_t* state[P2P_MAX];  // peers' p2p_state
+  int world, rank;
+};
+
 struct Ctx {
   // configuration
   int device = 0;
@@ -98,8 +112,10 @@ struct Ctx {
   bool p2p_ready = false;    // peer set-up attempted for the current allocation
   bool p2p_on = false;       // accelerations exchanged by peer stores inside the walk kernel (else ncclAllGather)
   P2P p2p = {};
-  uint32_t* p2p_state = nullptr;  // device: [0] epoch, [1] cta_done, [2] error, [4..4+P2P_MAX) flags
-  void* p2p_mapped[2 * P2P_MAX] = {};
+  uint32_t* p2p_state = nullptr;  // device: P2P_WORDS words, layout above
+  void* p2p_mapped[5 * P2P_MAX] = {};
+  P2PBuild p2pb = {};
+  int shard_k = 0;           // > 0: the build below level shard_k is sharded over the 2^shard_k ranks (this step)
   uint64_t acc_stride = 0;   // doubles per acc buffer
 
   // one step captured as a CUDA graph (replayed by kdnb_simple_sim when not profiling)

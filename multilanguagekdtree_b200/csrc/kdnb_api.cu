@@ -91,6 +91,12 @@ static void free_all(Ctx* c) {
     if (p) cudaFree(p);
     p = nullptr;
   };
+  // acc_t, p2p_state, nodes, perm and ms were exported with cudaIpcGetMemHandle: every rank closes its mappings of the
+  // peers' buffers and all ranks meet before anyone frees (freeing exported memory an importer still maps is undefined
+  // behaviour).  free_all runs from a growing plan() and from kdnb_destroy, both collective calls when world > 1.
+  const bool exported = c->p2p_on;
+  close_peers(c);
+  if (exported) peer_barrier(c);
   for (int d = 0; d < 3; ++d) {
     fr(c->pos[d]);
     fr(c->vel[d]);
@@ -118,12 +124,6 @@ static void free_all(Ctx* c) {
   fr(c->perm);
   fr(c->rank);
   c->posm = nullptr;  // lives inside the nodes allocation
-  // acc_t and p2p_state were exported with cudaIpcGetMemHandle: every rank closes its mappings of the peers' buffers
-  // and all ranks meet before anyone frees (freeing exported memory an importer still maps is undefined behaviour).
-  // free_all runs from a growing plan() and from kdnb_destroy, both collective calls when world > 1.
-  const bool exported = c->p2p_on;
-  close_peers(c);
-  if (exported) peer_barrier(c);
   fr(c->acc_t);
   fr(c->p2p_state);
   fr(c->wcounts);
@@ -135,7 +135,7 @@ static void free_all(Ctx* c) {
 
 // ---- peer-memory exchange set-up: cudaIpc handles of acc_t and of the flag array, all-gathered with NCCL
 static void close_peers(Ctx* c) {
-  for (int i = 0; i < 2 * P2P_MAX; ++i) {
+  for (int i = 0; i < 5 * P2P_MAX; ++i) {
     if (c->p2p_mapped[i]) cudaIpcCloseMemHandle(c->p2p_mapped[i]);
     c->p2p_mapped[i] = nullptr;
   }
@@ -167,15 +167,18 @@ static int setup_peers(Ctx* c) {
   struct Rec {
     int ok;
     int pad[15];
-    cudaIpcMemHandle_t acc, st;
+    cudaIpcMemHandle_t acc, st, nodes, perm, ms;
   };
-  static_assert(sizeof(Rec) == 192, "Rec");
+  static_assert(sizeof(Rec) == 384, "Rec");
   Rec mine;
   memset(&mine, 0, sizeof mine);
   mine.ok = (!disabled && W <= P2P_MAX) ? 1 : 0;
-  if (cudaMemsetAsync(c->p2p_state, 0, (4 + P2P_MAX) * sizeof(uint32_t), c->stream) != cudaSuccess) mine.ok = 0;
+  if (cudaMemsetAsync(c->p2p_state, 0, P2P_WORDS * sizeof(uint32_t), c->stream) != cudaSuccess) mine.ok = 0;
   if (mine.ok && cudaIpcGetMemHandle(&mine.acc, c->acc_t) != cudaSuccess) mine.ok = 0;
   if (mine.ok && cudaIpcGetMemHandle(&mine.st, c->p2p_state) != cudaSuccess) mine.ok = 0;
+  if (mine.ok && cudaIpcGetMemHandle(&mine.nodes, c->nodes) != cudaSuccess) mine.ok = 0;
+  if (mine.ok && cudaIpcGetMemHandle(&mine.perm, c->perm) != cudaSuccess) mine.ok = 0;
+  if (mine.ok && cudaIpcGetMemHandle(&mine.ms, c->ms) != cudaSuccess) mine.ok = 0;
   cudaGetLastError();
   Rec* dev = nullptr;
   int* dev2 = nullptr;
@@ -198,24 +201,32 @@ static int setup_peers(Ctx* c) {
   for (int k = 0; ok && k < W; ++k) ok = ok && all[k].ok;
   P2P pp;
   memset(&pp, 0, sizeof pp);
+  P2PBuild pb;
+  memset(&pb, 0, sizeof pb);
   for (int k = 0; ok && k < W; ++k) {
     if (k == c->rank_id) {
       pp.acc[k] = c->acc_t;
       pp.flags[k] = c->p2p_state + 4;
+      pb.nodes[k] = c->nodes, pb.perm[k] = c->perm, pb.ms[k] = c->ms, pb.state[k] = c->p2p_state;
       continue;
     }
-    void *pa = nullptr, *ps = nullptr;
-    if (cudaIpcOpenMemHandle(&pa, all[k].acc, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-        cudaIpcOpenMemHandle(&ps, all[k].st, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-      ok = false;
-      if (pa) cudaIpcCloseMemHandle(pa);
-      cudaGetLastError();
-      break;
+    void* m[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    const cudaIpcMemHandle_t* h[5] = {&all[k].acc, &all[k].st, &all[k].nodes, &all[k].perm, &all[k].ms};
+    for (int q = 0; ok && q < 5; ++q) {
+      if (cudaIpcOpenMemHandle(&m[q], *h[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        ok = false;
+        cudaGetLastError();
+      } else {
+        c->p2p_mapped[5 * k + q] = m[q];  // (closed by close_peers, also after a partial failure)
+      }
     }
-    c->p2p_mapped[2 * k] = pa;
-    c->p2p_mapped[2 * k + 1] = ps;
-    pp.acc[k] = reinterpret_cast<double*>(pa);
-    pp.flags[k] = reinterpret_cast<uint32_t*>(ps) + 4;
+    if (!ok) break;
+    pp.acc[k] = reinterpret_cast<double*>(m[0]);
+    pp.flags[k] = reinterpret_cast<uint32_t*>(m[1]) + 4;
+    pb.nodes[k] = reinterpret_cast<WNode*>(m[2]);
+    pb.perm[k] = reinterpret_cast<uint32_t*>(m[3]);
+    pb.ms[k] = reinterpret_cast<double4*>(m[4]);
+    pb.state[k] = reinterpret_cast<uint32_t*>(m[1]);
   }
   // second round: peer mode only if EVERY rank mapped every peer (otherwise all fall back to ncclAllGather)
   int okv = ok ? 1 : 0;
@@ -242,6 +253,9 @@ static int setup_peers(Ctx* c) {
   pp.world = W;
   pp.rank = c->rank_id;
   c->p2p = pp;
+  pb.world = W;
+  pb.rank = c->rank_id;
+  c->p2pb = pb;
   c->p2p_on = true;
   return 0;
 }
@@ -311,7 +325,7 @@ static int plan(Ctx* c, uint64_t n) {
     if (!rc) rc = dev_alloc(c, &c->rank, n);
     if (!rc) c->posm = reinterpret_cast<PosM*>(c->nodes + c->n_nodes);
     if (!rc) rc = dev_alloc(c, &c->acc_t, 2 * 3 * padded_slots(n));  // two buffers: peer exchange alternates by step parity
-    if (!rc) rc = dev_alloc(c, &c->p2p_state, 4 + P2P_MAX);
+    if (!rc) rc = dev_alloc(c, &c->p2p_state, P2P_WORDS);
     if (!rc && (c->flags & KDNB_FLAG_WALK_COUNTS)) rc = dev_alloc(c, &c->wcounts, 4 * n);
     if (!rc) rc = dev_alloc(c, &c->tmp3, 4 * n);
     if (!rc) rc = dev_alloc(c, &c->gcost, n / 32 + 2);

@@ -28,7 +28,7 @@ import build as simt_build  # noqa: E402
 lib = simt_build.build()
 fake = os.path.join(HERE, "_build", "libnccl.so.2")
 src = os.path.join(HERE, "fake_nccl.cpp")
-if not os.path.exists(fake) or os.path.getmtime(fake) < os.path.getmtime(src):
+if True:  # always rebuilt from fake_nccl.cpp (a second of g++): a stale or foreign binary of that name must never be loaded
     subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-Wl,-soname,libnccl.so.2", "-o", fake, src, "-lpthread"],
                    check=True)
 C.CDLL(fake, mode=C.RTLD_GLOBAL)                     # dlopen("libnccl.so.2") inside the library now finds this one
@@ -45,6 +45,7 @@ def rank_main(rank, world, uid, ics, steps, out, errs):
         sim.comm_init(uid, rank, world)
         sim.upload(ics)
         sim.build_tree()
+        nodes, idx = sim.tree()
         sim.calc_accel()
         acc = sim.accel()
         l0 = sim.launch_count
@@ -56,7 +57,7 @@ def rank_main(rank, world, uid, ics, steps, out, errs):
         sim.simple_sim_bodies_sharded(shard, n1, 1e-3, steps)
         assert shard.tobytes() == res[first:first + cnt].tobytes(), "sharded host path differs from the replicated path"
         sim.close()
-        out[rank] = (acc, res, launches)
+        out[rank] = (acc, res, launches, nodes, idx)
     except BaseException as e:  # noqa: BLE001
         errs.append((rank, repr(e)))
         raise
@@ -80,11 +81,14 @@ def main():
     with kd.KDTreeSim() as one:
         one.upload(ics)
         one.build_tree()
+        nodes1, idx1 = one.tree()
         one.calc_accel()
         acc1 = one.accel()
         one.simple_sim(1e-3, steps)
         res1 = one.download()
     for r in range(world):
+        assert out[r][4].tobytes() == idx1.tobytes(), f"rank {r}: tree order differs from the single-rank build"
+        assert out[r][3].tobytes() == nodes1.tobytes(), f"rank {r}: node records differ from the single-rank build"
         assert out[r][0].tobytes() == acc1.tobytes(), f"rank {r}: accelerations differ from the single-rank walk"
         assert out[r][1].tobytes() == res1.tobytes(), f"rank {r}: trajectory differs from the single-rank run"
     mode = "ncclAllGather exchange" if os.environ.get("SIMT_IPC") == "0" or os.environ.get("KDNB_NO_P2P") else "peer stores"

@@ -6,7 +6,9 @@
 
 Every rank builds the (replicated) tree, walks its shard of tree slots, all-gathers the accelerations with NCCL and
 kick/drifts everything; the result must be BIT-IDENTICAL on every rank and identical to a single-GPU run, because the
-same arithmetic is applied to every particle wherever it is walked."""
+same arithmetic is applied to every particle wherever it is walked.  KDNB_SHARD_BUILD=1 forces the sharded tree build
+(every rank builds one subtree below the top log2(world) levels and pushes it to its peers): the tree — node records and
+tree order — must then be bit-identical on every rank and to the single-GPU build as well."""
 import os
 import sys
 
@@ -31,6 +33,7 @@ def main():
     sim.comm_init(ids[0], rank, world)
     sim.upload(ics)
     sim.build_tree()
+    nodes, idx = sim.tree()
     sim.calc_accel()
     acc = sim.accel()
     sim.simple_sim(1e-3, steps)
@@ -42,17 +45,21 @@ def main():
     assert shard.tobytes() == out[first:first + cnt].tobytes(), "sharded host path differs from the replicated path"
     sim.close()
     blobs = [None] * world
-    dist.all_gather_object(blobs, (out.tobytes(), acc.tobytes()))
+    import hashlib
+    tree_digest = hashlib.sha256(nodes.tobytes() + idx.tobytes()).hexdigest()
+    dist.all_gather_object(blobs, (out.tobytes(), acc.tobytes(), tree_digest))
     if rank == 0:
         for r in range(1, world):
             assert blobs[r] == blobs[0], f"rank {r} differs from rank 0"
         with kd.KDTreeSim(device=local) as one:
             one.upload(ics)
             one.build_tree()
+            nodes1, idx1 = one.tree()
             one.calc_accel()
             acc1 = one.accel()
             one.simple_sim(1e-3, steps)
             out1 = one.download()
+        assert hashlib.sha256(nodes1.tobytes() + idx1.tobytes()).hexdigest() == tree_digest, "tree differs from the single-GPU build"
         assert acc1.tobytes() == acc.tobytes(), "sharded accelerations differ from the single-GPU walk"
         assert out1.tobytes() == out.tobytes(), "sharded trajectory differs from the single-GPU trajectory"
         print(f"multigpu_check ok: world={world} n={n + 1} steps={steps}: all ranks and the 1-GPU run are bit-identical")
