@@ -31,14 +31,19 @@ struct P2P {
 // Sharded tree build (multi-GPU, peer mode, world = 2^k): the top k levels are built by every rank, below them rank r
 // builds only the subtree of level-k segment r and stores its node records, its slice of the tree order (perm) and its
 // root's mass sums straight into every peer's buffers; a flag per rank publishes them (build.cu).
+// Split sort (multi-GPU, peer mode): a rank sorts only every m-th non-flat dimension (m = min(world, dimensions)), leaves
+// its sorted lists in an export buffer and fetches the others from a peer that sorted them (sort.cu).
 // p2p_state words: [0] acc epoch, [1] acc cta_done, [2] error, [4..20) acc flags, [20..36) build flags, [36] build epoch,
-// [37] build cta_done
-constexpr int P2P_BFLAGS = 4 + P2P_MAX, P2P_BEPOCH = 4 + 2 * P2P_MAX, P2P_BDONE = 5 + 2 * P2P_MAX, P2P_WORDS = 8 + 2 * P2P_MAX;
+// [37] build cta_done, [38..54) sort flags, [54] sort epoch, [55] export cta_done, [56] fetch cta_done
+constexpr int P2P_BFLAGS = 4 + P2P_MAX, P2P_BEPOCH = 4 + 2 * P2P_MAX, P2P_BDONE = 5 + 2 * P2P_MAX;
+constexpr int P2P_SFLAGS = 6 + 2 * P2P_MAX, P2P_SEPOCH = 6 + 3 * P2P_MAX, P2P_SDONE = 7 + 3 * P2P_MAX, P2P_FDONE = 8 + 3 * P2P_MAX,
+              P2P_WORDS = 12 + 3 * P2P_MAX;
 struct P2PBuild {
   WNode* nodes[P2P_MAX];     // peers' node arrays, own included
   uint32_t* perm[P2P_MAX];   // peers' tree order
   double4* ms[P2P_MAX];      // peers' per-node mass sums
   uint32_t* state[P2P_MAX];  // peers' p2p_state
+  uint32_t* sexp[P2P_MAX];   // peers' sorted-list export buffers ([3][n] ids; their keys[1], dead between two sorts)
   int world, rank;
 };
 
@@ -78,6 +83,7 @@ struct Ctx {
   uint32_t* hist = nullptr;                // [3][256][ntiles]
   uint32_t* digit_tot = nullptr;           // [3][256]
   uint32_t* flat = nullptr;                // [3] 1 = all coordinates of that dimension equal (lives behind digit_tot); [3] planar walk
+  uint32_t* dmask = nullptr;               // [0..2] 1 = this rank does not sort dimension d (flat, or a peer's share of the split sort); [4..6] the peer to fetch it from (behind flat)
   uint64_t* sort_state = nullptr;          // [SS_WORDS] 32-bit key scaling, need64 flag, running position extents (common.cuh)
   bool extent_fresh = false;               // the extent records describe the current positions and were not consumed yet
   uint32_t* rk = nullptr;                  // [3][n] rank of every particle in the initial sorted list of each dimension
@@ -113,8 +119,9 @@ struct Ctx {
   bool p2p_on = false;       // accelerations exchanged by peer stores inside the walk kernel (else ncclAllGather)
   P2P p2p = {};
   uint32_t* p2p_state = nullptr;  // device: P2P_WORDS words, layout above
-  void* p2p_mapped[5 * P2P_MAX] = {};
+  void* p2p_mapped[6 * P2P_MAX] = {};
   P2PBuild p2pb = {};
+  bool split_sort = false;   // the last sort_prep assigned the dimensions for a split sort
   int shard_k = 0;           // > 0: the build below level shard_k is sharded over the 2^shard_k ranks (this step)
   uint64_t acc_stride = 0;   // doubles per acc buffer
 

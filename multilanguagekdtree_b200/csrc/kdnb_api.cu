@@ -91,7 +91,7 @@ static void free_all(Ctx* c) {
     if (p) cudaFree(p);
     p = nullptr;
   };
-  // acc_t, p2p_state, nodes, perm and ms were exported with cudaIpcGetMemHandle: every rank closes its mappings of the
+  // acc_t, p2p_state, nodes, perm, ms and keys[1] were exported with cudaIpcGetMemHandle: every rank closes its mappings of the
   // peers' buffers and all ranks meet before anyone frees (freeing exported memory an importer still maps is undefined
   // behaviour).  free_all runs from a growing plan() and from kdnb_destroy, both collective calls when world > 1.
   const bool exported = c->p2p_on;
@@ -135,7 +135,7 @@ static void free_all(Ctx* c) {
 
 // ---- peer-memory exchange set-up: cudaIpc handles of acc_t and of the flag array, all-gathered with NCCL
 static void close_peers(Ctx* c) {
-  for (int i = 0; i < 5 * P2P_MAX; ++i) {
+  for (int i = 0; i < 6 * P2P_MAX; ++i) {
     if (c->p2p_mapped[i]) cudaIpcCloseMemHandle(c->p2p_mapped[i]);
     c->p2p_mapped[i] = nullptr;
   }
@@ -167,9 +167,9 @@ static int setup_peers(Ctx* c) {
   struct Rec {
     int ok;
     int pad[15];
-    cudaIpcMemHandle_t acc, st, nodes, perm, ms;
+    cudaIpcMemHandle_t acc, st, nodes, perm, ms, sexp;
   };
-  static_assert(sizeof(Rec) == 384, "Rec");
+  static_assert(sizeof(Rec) == 448, "Rec");
   Rec mine;
   memset(&mine, 0, sizeof mine);
   mine.ok = (!disabled && W <= P2P_MAX) ? 1 : 0;
@@ -179,6 +179,7 @@ static int setup_peers(Ctx* c) {
   if (mine.ok && cudaIpcGetMemHandle(&mine.nodes, c->nodes) != cudaSuccess) mine.ok = 0;
   if (mine.ok && cudaIpcGetMemHandle(&mine.perm, c->perm) != cudaSuccess) mine.ok = 0;
   if (mine.ok && cudaIpcGetMemHandle(&mine.ms, c->ms) != cudaSuccess) mine.ok = 0;
+  if (mine.ok && cudaIpcGetMemHandle(&mine.sexp, c->keys[1]) != cudaSuccess) mine.ok = 0;
   cudaGetLastError();
   Rec* dev = nullptr;
   int* dev2 = nullptr;
@@ -208,16 +209,17 @@ static int setup_peers(Ctx* c) {
       pp.acc[k] = c->acc_t;
       pp.flags[k] = c->p2p_state + 4;
       pb.nodes[k] = c->nodes, pb.perm[k] = c->perm, pb.ms[k] = c->ms, pb.state[k] = c->p2p_state;
+      pb.sexp[k] = reinterpret_cast<uint32_t*>(c->keys[1]);
       continue;
     }
-    void* m[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    const cudaIpcMemHandle_t* h[5] = {&all[k].acc, &all[k].st, &all[k].nodes, &all[k].perm, &all[k].ms};
-    for (int q = 0; ok && q < 5; ++q) {
+    void* m[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const cudaIpcMemHandle_t* h[6] = {&all[k].acc, &all[k].st, &all[k].nodes, &all[k].perm, &all[k].ms, &all[k].sexp};
+    for (int q = 0; ok && q < 6; ++q) {
       if (cudaIpcOpenMemHandle(&m[q], *h[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
         ok = false;
         cudaGetLastError();
       } else {
-        c->p2p_mapped[5 * k + q] = m[q];  // (closed by close_peers, also after a partial failure)
+        c->p2p_mapped[6 * k + q] = m[q];  // (closed by close_peers, also after a partial failure)
       }
     }
     if (!ok) break;
@@ -227,6 +229,7 @@ static int setup_peers(Ctx* c) {
     pb.perm[k] = reinterpret_cast<uint32_t*>(m[3]);
     pb.ms[k] = reinterpret_cast<double4*>(m[4]);
     pb.state[k] = reinterpret_cast<uint32_t*>(m[1]);
+    pb.sexp[k] = reinterpret_cast<uint32_t*>(m[5]);
   }
   // second round: peer mode only if EVERY rank mapped every peer (otherwise all fall back to ncclAllGather)
   int okv = ok ? 1 : 0;
@@ -305,8 +308,9 @@ static int plan(Ctx* c, uint64_t n) {
     if (!rc) rc = dev_alloc(c, &c->list[0], 3 * n);
     if (!rc) rc = dev_alloc(c, &c->list[1], 3 * n);
     if (!rc) rc = dev_alloc(c, &c->hist, 3ull * 256 * c->ntiles);
-    if (!rc) rc = dev_alloc(c, &c->digit_tot, 3 * 256 + 4);
+    if (!rc) rc = dev_alloc(c, &c->digit_tot, 3 * 256 + 16);
     if (!rc) c->flat = c->digit_tot + 3 * 256;
+    if (!rc) c->dmask = c->flat + 4;
     if (!rc) rc = dev_alloc(c, &c->sort_state, SS_WORDS);
     if (!rc) rc = dev_alloc(c, &c->rk, 3 * n);
     if (!rc) rc = dev_alloc(c, &c->pm, n);

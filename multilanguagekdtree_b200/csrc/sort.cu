@@ -237,10 +237,12 @@ __global__ void __launch_bounds__(SORT_THREADS, 8) sort_downsweep(Pos3 pos, cons
 //    orders the leaves;
 //  * flat[3] = 1 when, in addition, every z is +-0 and every mass is > 0 (the masses are seen at upload only): then every node's centre-of-mass z (sum m*z / sum m) is +-0 as well, dz == 0 in every test and
 //    interaction, and the walk skips the z terms (walk2.cuh).
-__global__ void __launch_bounds__(EXT_PARTS) sort_prep(uint64_t* ss, uint32_t* flat) {
+__global__ void __launch_bounds__(EXT_PARTS) sort_prep(uint64_t* ss, uint32_t* flat, uint32_t* dmask, int rank, int split_world,
+                                                      int consume) {
   pdl_sync();
   __shared__ uint64_t sm[8][8];
   uint64_t v[7];
+  if (consume) {  // (consume == 0: only the dimension shares of the split sort are re-derived, from the flags that stand)
   {
     uint64_t* rec = ss + SS_PART + 8 * threadIdx.x;  // one record per thread
 #pragma unroll
@@ -256,14 +258,15 @@ __global__ void __launch_bounds__(EXT_PARTS) sort_prep(uint64_t* ss, uint32_t* f
     if (lane == 0) sm[w][j] = r;
   }
   __syncthreads();
+  }
   if (threadIdx.x == 0) {
     uint64_t t[7];
-    for (int j = 0; j < 7; ++j) {
+    for (int j = 0; consume && j < 7; ++j) {
       t[j] = sm[0][j];
       for (int q = 1; q < 8; ++q) t[j] = j < 3 ? (sm[q][j] < t[j] ? sm[q][j] : t[j]) : (sm[q][j] > t[j] ? sm[q][j] : t[j]);
     }
     uint64_t need64 = 0ull;
-    for (int d = 0; d < 3; ++d) {
+    for (int d = 0; consume && d < 3; ++d) {
       const double lo = key_to_f64(t[d]), hi = key_to_f64(t[3 + d]);
       double scale = 0.0;  // all keys 0 when the extent is 0: one run of equal coordinates, already in id order
       if (!(fabs(lo) <= 1.7976931348623157e308) || !(fabs(hi) <= 1.7976931348623157e308)) need64 = 1ull;
@@ -272,10 +275,111 @@ __global__ void __launch_bounds__(EXT_PARTS) sort_prep(uint64_t* ss, uint32_t* f
       ss[SS_SCALE + d] = (uint64_t)__double_as_longlong(scale);
       flat[d] = (d > 0 && t[d] == t[3 + d]) ? 1u : 0u;
     }
-    ss[SS_NEED64] = need64;
-    if (t[6] < 2ull) ss[SS_LIGHT] = t[6];  // an upload's records (a kick leaves 2: the masses did not change)
-    const uint64_t light = ss[SS_LIGHT];
-    flat[3] = (t[2] == t[5] && t[2] == f64_key(0.0) && light == 0ull) ? 1u : 0u;
+    if (consume) {
+      ss[SS_NEED64] = need64;
+      if (t[6] < 2ull) ss[SS_LIGHT] = t[6];  // an upload's records (a kick leaves 2: the masses did not change)
+      const uint64_t light = ss[SS_LIGHT];
+      flat[3] = (t[2] == t[5] && t[2] == f64_key(0.0) && light == 0ull) ? 1u : 0u;
+    }
+    // split sort (split_world > 1): this rank sorts the non-flat dimensions whose index among them is congruent to its
+    // rank modulo m = min(world, their number) and fetches every other one from the rank of its own block of m that
+    // sorted it (sort_export / sort_fetch below)
+    uint32_t nact = 0;
+    for (int d = 0; d < 3; ++d) nact += flat[d] ? 0u : 1u;
+    const uint32_t m = split_world > 1 ? min((uint32_t)split_world, nact) : 1u;
+    uint32_t idx = 0;
+    for (int d = 0; d < 3; ++d) {
+      uint32_t skip = flat[d], src = 0xffffffffu;
+      if (!flat[d]) {
+        if (m > 1 && (idx % m) != ((uint32_t)rank % m)) {
+          skip = 1u;
+          src = (uint32_t)rank - (uint32_t)rank % m + idx % m;
+          if (src >= (uint32_t)split_world) src = idx % m;
+        }
+        ++idx;
+      }
+      dmask[d] = skip;
+      dmask[4 + d] = src;
+    }
+  }
+}
+
+// Split sort, donor side: the lists this rank sorted go to its export buffer (the list buffers themselves are permuted
+// by the level partitions while peers would still be reading them); a system-scope fence and the last CTA then raise
+// this rank's sort flag on every peer.
+__global__ void __launch_bounds__(256) sort_export_kernel(P2PBuild pb, const uint32_t* __restrict__ lists, uint32_t n,
+                                                          const uint32_t* __restrict__ dmask) {
+  pdl_sync();
+  const int me = pb.rank;
+  uint32_t* out = pb.sexp[me];
+  for (int d = 0; d < 3; ++d) {
+    if (dmask[d]) continue;
+    // (n is not a multiple of 4 in general and d * n not 16-byte aligned: vector body on the aligned part, scalar ends)
+    const uint64_t base = (uint64_t)d * n;
+    const uint64_t a0 = (4 - (base & 3)) & 3;  // elements until lists + base is 16-byte aligned
+    const uint64_t nv = n > a0 ? (n - a0) / 4 : 0;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = tid; i < nv; i += nthr)
+      reinterpret_cast<uint4*>(out + base + a0)[i] = reinterpret_cast<const uint4*>(lists + base + a0)[i];
+    for (uint64_t i = tid; i < n; i += nthr)
+      if (i < a0 || i >= a0 + 4 * nv) out[base + i] = lists[base + i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t* st = pb.state[me];
+    const uint32_t done = atomicAdd(&st[P2P_SDONE], 1u);
+    if (done == gridDim.x - 1) {
+      st[P2P_SDONE] = 0;
+      __threadfence_system();
+      const uint32_t epoch = st[P2P_SEPOCH];
+      for (int p = 0; p < pb.world; ++p) *reinterpret_cast<volatile uint32_t*>(pb.state[p] + P2P_SFLAGS + me) = epoch + 1u;
+    }
+  }
+}
+
+// Split sort, receiving side: every dimension this rank did not sort is read from the export buffer of the peer that
+// did, once that peer's flag says it is there.  The last CTA moves this rank's sort epoch on.  (No acknowledgement: a
+// donor overwrites its export buffer in its NEXT sort, which starts after the step's all-rank exchange of the
+// accelerations, and that exchange is behind this kernel on every rank.)
+__global__ void __launch_bounds__(256) sort_fetch_kernel(P2PBuild pb, uint32_t* __restrict__ lists, uint32_t n,
+                                                         const uint32_t* __restrict__ dmask) {
+  pdl_sync();
+  const int me = pb.rank;
+  uint32_t* st = pb.state[me];
+  const uint32_t target = st[P2P_SEPOCH] + 1u;
+  for (int d = 0; d < 3; ++d) {
+    const uint32_t src = dmask[4 + d];
+    if (src == 0xffffffffu) continue;
+    if (threadIdx.x == 0) {
+      volatile uint32_t* flag = st + P2P_SFLAGS + src;
+      const long long t0 = clock64();
+      while (*flag < target) {
+        if (clock64() - t0 > (30LL << 30)) {  // ~15 s: the donor died; record it instead of hanging for ever
+          st[2] = 1u;
+          break;
+        }
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    const uint64_t base = (uint64_t)d * n;
+    const uint32_t* in = pb.sexp[src] + base;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t a0 = (4 - (base & 3)) & 3;
+    const uint64_t nv = n > a0 ? (n - a0) / 4 : 0;
+    for (uint64_t i = tid; i < nv; i += nthr)
+      reinterpret_cast<uint4*>(lists + base + a0)[i] = reinterpret_cast<const uint4*>(in + a0)[i];
+    for (uint64_t i = tid; i < n; i += nthr)
+      if (i < a0 || i >= a0 + 4 * nv) lists[base + i] = in[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t done = atomicAdd(&st[P2P_FDONE], 1u);
+    if (done == gridDim.x - 1) {
+      st[P2P_FDONE] = 0;
+      st[P2P_SEPOCH] = target;
+    }
   }
 }
 
@@ -366,20 +470,20 @@ static void sort_passes(Ctx* c, Pos3 pos, bool gated) {
     const int shift = 8 * pass;
     const int src = (pass & 1) ? 1 : 0, dst = src ^ 1;  // pass 0 reads positions, writes buf1
     if (pass == 0) {
-      KDNB_LAUNCH(c, (sort_upsweep<true, K>), gt, SORT_THREADS, 0, pos, nullptr, n, shift, nt, c->hist, c->flat, ss, gated);
+      KDNB_LAUNCH(c, (sort_upsweep<true, K>), gt, SORT_THREADS, 0, pos, nullptr, n, shift, nt, c->hist, c->dmask, ss, gated);
     } else {
-      KDNB_LAUNCH(c, (sort_upsweep<false, K>), gt, SORT_THREADS, 0, pos, kb[src], n, shift, nt, c->hist, c->flat, ss, gated);
+      KDNB_LAUNCH(c, (sort_upsweep<false, K>), gt, SORT_THREADS, 0, pos, kb[src], n, shift, nt, c->hist, c->dmask, ss, gated);
     }
-    KDNB_LAUNCH(c, sort_scan_rows, gs, 256, 0, c->hist, nt, c->digit_tot, c->flat, ss, gated);
+    KDNB_LAUNCH(c, sort_scan_rows, gs, 256, 0, c->hist, nt, c->digit_tot, c->dmask, ss, gated);
     if (pass == 0) {
       KDNB_LAUNCH(c, (sort_downsweep<true, false, K>), gt, SORT_THREADS, 0, pos, nullptr, nullptr, kb[1], c->list[1], n,
-                  shift, nt, c->hist, c->digit_tot, c->flat, ss, gated);
+                  shift, nt, c->hist, c->digit_tot, c->dmask, ss, gated);
     } else if (pass == passes - 1 && sizeof(K) == 8) {  // (the 32-bit keys of the last pass are read by sort_fixup)
       KDNB_LAUNCH(c, (sort_downsweep<false, true, K>), gt, SORT_THREADS, 0, pos, kb[src], c->list[src], kb[dst],
-                  c->list[dst], n, shift, nt, c->hist, c->digit_tot, c->flat, ss, gated);
+                  c->list[dst], n, shift, nt, c->hist, c->digit_tot, c->dmask, ss, gated);
     } else {
       KDNB_LAUNCH(c, (sort_downsweep<false, false, K>), gt, SORT_THREADS, 0, pos, kb[src], c->list[src], kb[dst],
-                  c->list[dst], n, shift, nt, c->hist, c->digit_tot, c->flat, ss, gated);
+                  c->list[dst], n, shift, nt, c->hist, c->digit_tot, c->dmask, ss, gated);
     }
   }
 }
@@ -447,14 +551,24 @@ int sort_lists(Ctx* c) {
   static const bool stubs = knob && std::string(knob) == "stubs";
   // key scaling and flat / planar flags from the extents accumulated by whoever wrote the positions (upload or the
   // previous kick); a rebuild on unchanged positions keeps what the previous build derived
-  if (c->extent_fresh) KDNB_LAUNCH(c, sort_prep, 1, EXT_PARTS, 0, c->sort_state, c->flat);
+  // Split sort (multi-GPU, peer mode): every rank sorts a share of the dimensions and fetches the rest from a peer.
+  // KDNB_SORT_SPLIT=0 disables, =1 forces it at every size.
+  static const int split_mode = [] {
+    const char* e = getenv("KDNB_SORT_SPLIT");
+    return e ? (atoi(e) != 0 ? 1 : 0) : -1;
+  }();
+  const bool split = c->world > 1 && c->p2p_on && c->l0 > 0 && (split_mode == 1 || (split_mode < 0 && c->n >= (2ull << 20)));
+  if (c->extent_fresh || split != c->split_sort)
+    KDNB_LAUNCH(c, sort_prep, 1, EXT_PARTS, 0, c->sort_state, c->flat, c->dmask, c->rank_id, split ? c->world : 0,
+                c->extent_fresh ? 1 : 0);
+  c->split_sort = split;
   c->extent_fresh = false;
   if (only64) {
     sort_passes<uint64_t>(c, pos, false);
   } else {
     sort_passes<uint32_t>(c, pos, false);
     KDNB_LAUNCH(c, sort_fixup, dim3((n + 255) / 256, 3), 256, 0, pos, reinterpret_cast<const uint32_t*>(c->keys[0]),
-                c->list[0], n, c->flat, c->sort_state);
+                c->list[0], n, c->dmask, c->sort_state);
     // the 64-bit passes run only when need64 was raised: decided by the host between plain launches (one stream
     // synchronisation), by a conditional node inside a captured step, by the kernels themselves otherwise
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
@@ -469,6 +583,10 @@ int sort_lists(Ctx* c) {
       KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
       if (need) sort_passes<uint64_t>(c, pos, false);
     }
+  }
+  if (split) {
+    KDNB_LAUNCH(c, sort_export_kernel, 2 * c->num_sms, 256, 0, c->p2pb, c->list[0], n, c->dmask);
+    KDNB_LAUNCH(c, sort_fetch_kernel, 2 * c->num_sms, 256, 0, c->p2pb, c->list[0], n, c->dmask);
   }
   if (c->l0 > 0) KDNB_LAUNCH(c, rank_from_lists, dim3((n + 255) / 256, 3), 256, 0, c->list[0], n, c->rk, c->flat);
   KDNB_CHECK_LAUNCH(c);

@@ -51,3 +51,35 @@ def test_ranks_with_empty_shards_under_the_simt_model():
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "devtools", "simt", "multirank.py"), world, n, "2"],
                            capture_output=True, text=True, cwd=ROOT, timeout=300)
         assert r.returncode == 0 and f"multirank ok: world={world}" in r.stdout, (r.stdout + r.stderr)[-2000:]
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world", ["2", "4"])
+def test_sharded_tree_build_under_the_simt_model(world):
+    """The sharded build of the multi-GPU path (build.cu: every rank builds one subtree below the top log2(world) levels,
+    pushes its node records and tree order to the peers, gathers the foreign particle copies itself), forced at a small
+    size: every rank's tree — node records and tree order —, accelerations and trajectory must be bit-identical to a
+    single-rank run (tests/devtools/simt/multirank.py compares all of them)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "devtools", "simt", "multirank.py"), world, "9000", "2"],
+                       capture_output=True, text=True, cwd=ROOT, env={**os.environ, "KDNB_SHARD_BUILD": "1", "KDNB_SORT_SPLIT": "0"})
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0 and f"multirank ok: world={world}" in r.stdout, tail
+    # the sharded path really ran: it adds four launches per step (push, wait, foreign gather, top levels' sums)
+    import re
+    launches = float(re.search(r"([0-9.]+) kernel launches per step", r.stdout).group(1))
+    r0 = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "devtools", "simt", "multirank.py"), world, "9000", "2"],
+                        capture_output=True, text=True, cwd=ROOT, env={**os.environ, "KDNB_SHARD_BUILD": "0", "KDNB_SORT_SPLIT": "0"})
+    base = float(re.search(r"([0-9.]+) kernel launches per step", r0.stdout).group(1))
+    assert launches > base + 3.5, (launches, base)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world", ["2", "3"])
+def test_split_sort_under_the_simt_model(world):
+    """The split sort of the multi-GPU path (sort.cu: a rank sorts only its share of the non-flat dimensions, exports the
+    lists and fetches the others from a peer), forced at a small size together with the sharded build: trees,
+    accelerations and trajectories bit-identical to a single-rank run on every rank."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "devtools", "simt", "multirank.py"), world, "9000", "2"],
+                       capture_output=True, text=True, cwd=ROOT, env={**os.environ, "KDNB_SHARD_BUILD": "1", "KDNB_SORT_SPLIT": "1"})
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0 and f"multirank ok: world={world}" in r.stdout, tail
