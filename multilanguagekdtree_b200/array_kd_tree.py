@@ -124,6 +124,11 @@ class KDTreeSim:
         assert shard.dtype == PARTICLE and shard.flags.c_contiguous
         self._ck(self._L.kdnb_simple_sim_bodies_sharded(self._h, shard.ctypes.data, total, dt, steps), "kdnb_simple_sim_bodies_sharded")
 
+    def upload_sharded(self, shard: np.ndarray, total: int) -> None:
+        """Multi-GPU: upload this rank's host slice; the other slices arrive over NVLink (kdnb_upload_particles_sharded)."""
+        assert shard.dtype == PARTICLE and shard.flags.c_contiguous
+        self._ck(self._L.kdnb_upload_particles_sharded(self._h, shard.ctypes.data, total), "kdnb_upload_particles_sharded")
+
     def synchronize(self) -> None:
         self._ck(self._L.kdnb_synchronize(self._h), "kdnb_synchronize")
 

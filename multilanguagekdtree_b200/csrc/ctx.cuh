@@ -57,6 +57,9 @@ struct Ctx {
   uint32_t flags = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t side_stream = nullptr;  // captures conditional-node bodies (sort.cu)
+  cudaStream_t order_stream = nullptr; // the walk's launch-order kernel, next to the build (walk.cu)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool order_pending = false;
 
   // sizes
   uint64_t n = 0;        // particles (N+1 of the reference)
@@ -156,6 +159,7 @@ int export_tree(Ctx* c, kdnb_node* dev_out);
 void init_unused_nodes(Ctx* c);
 // walk.cu
 int walk(Ctx* c);
+void walk_order_fork(Ctx* c);
 // kick.cu
 int kick_drift(Ctx* c, double dt);
 int p2p_wait_step(Ctx* c);

@@ -392,6 +392,7 @@ static int one_step(Ctx* c, double dt, bool capturing = false) {
     if (prof) cudaEventRecordWithFlags(c->pev[k], c->stream, capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
   };
   mark(0);
+  walk_order_fork(c);                     // (the walk's launch order, from the previous walk: on a side stream next to the build)
   if (int rc = build_tree(c)) return rc;  // indices reset + build_tree_par4 (:641-643)
   mark(1);
   if (int rc = walk(c)) return rc;        // calc_accel for every particle (:647)
@@ -463,6 +464,9 @@ kdnb_ctx* kdnb_create(const kdnb_config* cfg) {
   if ((e = cudaSetDevice(c->device)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&c->order_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreate(&c->sw_begin)) != cudaSuccess || (e = cudaEventCreate(&c->sw_end)) != cudaSuccess) {
     g_create_error = std::string("CUDA init: ") + cudaGetErrorString(e);
     delete h;
@@ -489,6 +493,9 @@ void kdnb_destroy(kdnb_ctx* ctx) {
   if (c->sw_end) cudaEventDestroy(c->sw_end);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->side_stream) cudaStreamDestroy(c->side_stream);
+  if (c->order_stream) cudaStreamDestroy(c->order_stream);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete ctx;
 }
 

@@ -33,6 +33,55 @@ int p2p_wait_step(Ctx* c) {
   return 0;
 }
 
+// this rank's share of the tree slots
+static void walk_range(const Ctx* c, uint32_t* begin, uint32_t* end) {
+  *begin = 0, *end = (uint32_t)c->n;
+  if (c->world > 1) {
+    *begin = (uint32_t)std::min<uint64_t>(c->n, (uint64_t)c->rank_id * c->shard_slots);
+    *end = (uint32_t)std::min<uint64_t>(c->n, (uint64_t)(c->rank_id + 1) * c->shard_slots);
+  }
+}
+
+// Heaviest-first launch order from the work the groups reported in the previous walk of the same particle set and
+// shard (the tree order moves little from step to step).  Production kernel only, and only while the node records
+// and tree-ordered particles (~66 B per particle) fit the 126 MB L2: the index order is also the spatial order, so
+// the ~3500 groups in flight share their near field; with the cost order they are scattered over the whole domain,
+// which costs nothing when the tree is L2-resident (measured at N = 125k and 1M) and loses where it is not (N = 10M
+// streams the tree from HBM: 20.69 ms in index order, 20.99 ms heaviest first, profiles/r02_ab_walk_lpt_10M.txt) —
+// there the launch stays in index order.  KDNB_WALK_LPT=0 disables, =1 forces it at every size.
+static bool walk_uses_order(const Ctx* c, uint32_t begin, uint32_t end) {
+  static const int lpt_mode = [] {
+    const char* s = getenv("KDNB_WALK_LPT");
+    return s ? (atoi(s) != 0 ? 1 : 0) : -1;
+  }();
+  constexpr uint64_t LPT_MAX_N = 1ull << 21;
+  const bool lpt = lpt_mode == 1 || (lpt_mode < 0 && c->n <= LPT_MAX_N);
+  const bool production = !(c->flags & (KDNB_FLAG_WALK_COUNTS | KDNB_FLAG_EXACT_MATH));
+  return production && lpt && end > begin;
+}
+static bool walk_has_costs(const Ctx* c, uint32_t begin, uint32_t end) {
+  return c->gcost_n == c->n && c->gcost_begin == begin && c->gcost_end == end && (end - begin + 31) / 32 > 1;
+}
+
+// The order kernel (one CTA, ~27 us at N = 1M) depends only on the previous walk: a step starts it on a side stream
+// next to the tree build and the walk waits for it (a fork / join inside the step graph).
+void walk_order_fork(Ctx* c) {
+  uint32_t begin, end;
+  walk_range(c, &begin, &end);
+  c->order_pending = false;
+  if (!c->order_stream || !walk_uses_order(c, begin, end) || !walk_has_costs(c, begin, end)) return;
+  if (cudaEventRecord(c->ev_fork, c->stream) != cudaSuccess || cudaStreamWaitEvent(c->order_stream, c->ev_fork, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  cudaStream_t keep = c->stream;
+  c->stream = c->order_stream;
+  KDNB_LAUNCH(c, walk_order_kernel, 1, 1024, 0, c->gcost, c->gorder, (end - begin + 31) / 32);
+  c->stream = keep;
+  cudaEventRecord(c->ev_join, c->order_stream);
+  c->order_pending = true;
+}
+
 static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
   const uint32_t grid = std::max<uint32_t>((end - begin + 31) / 32, 1u);
   const bool counts = (c->flags & KDNB_FLAG_WALK_COUNTS) != 0;
@@ -41,24 +90,13 @@ static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
   if (!c->p2p_on) pp.world = 0;
   int lshift = 0;  // lanes per leaf in the leaf rounds: the smallest power of two >= MAX_PARTS
   while ((1u << lshift) < c->mp) ++lshift;
-  // Heaviest-first launch order from the work the groups reported in the previous walk of the same particle set and
-  // shard (the tree order moves little from step to step).  Production kernel only, and only while the node records
-  // and tree-ordered particles (~66 B per particle) fit the 126 MB L2: the index order is also the spatial order, so
-  // the ~3500 groups in flight share their near field; with the cost order they are scattered over the whole domain,
-  // which costs nothing when the tree is L2-resident (measured at N = 125k and 1M) but has not been measured where it
-  // is not (N >= 10M streams the tree from HBM) — there the launch stays in index order.
-  // KDNB_WALK_LPT=0 disables, =1 forces it at every size.
-  static const int lpt_mode = [] {
-    const char* s = getenv("KDNB_WALK_LPT");
-    return s ? (atoi(s) != 0 ? 1 : 0) : -1;
-  }();
-  constexpr uint64_t LPT_MAX_N = 1ull << 21;
-  const bool lpt = lpt_mode == 1 || (lpt_mode < 0 && c->n <= LPT_MAX_N);
-  const bool production = !exact && !counts;
   const uint32_t* gorder = nullptr;
   uint32_t* gcost = nullptr;
-  if (production && lpt) {
-    if (c->gcost_n == c->n && c->gcost_begin == begin && c->gcost_end == end && grid > 1) {
+  if (walk_uses_order(c, begin, end)) {
+    if (c->order_pending) {  // started by walk_order_fork at the beginning of this step
+      cudaStreamWaitEvent(c->stream, c->ev_join, 0);
+      gorder = c->gorder;
+    } else if (walk_has_costs(c, begin, end)) {
       KDNB_LAUNCH(c, walk_order_kernel, 1, 1024, 0, c->gcost, c->gorder, grid);
       gorder = c->gorder;
     }
@@ -67,6 +105,7 @@ static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
     c->gcost_begin = begin;
     c->gcost_end = end;
   }
+  c->order_pending = false;
 #define KDNB_WALK_ARGS c->nodes, c->posm, c->acc_t, begin, end, c->theta2, c->wcounts, pp, c->flat, lshift, gorder, gcost
   const bool peer = pp.world > 1;
   if (exact && counts)
@@ -94,12 +133,8 @@ static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
 }
 
 int walk(Ctx* c) {
-  const uint32_t n = (uint32_t)c->n;
-  uint32_t begin = 0, end = n;
-  if (c->world > 1) {
-    begin = (uint32_t)std::min<uint64_t>(c->n, (uint64_t)c->rank_id * c->shard_slots);
-    end = (uint32_t)std::min<uint64_t>(c->n, (uint64_t)(c->rank_id + 1) * c->shard_slots);
-  }
+  uint32_t begin, end;
+  walk_range(c, &begin, &end);
   // (peer mode: a rank whose shard is empty — fewer particles than 64 x (world - 1) — still launches one CTA, which has
   // nothing to walk but raises this rank's flag on every peer; without it all ranks would wait for the flag until the
   // wait kernel's timeout, every step)
