@@ -566,7 +566,10 @@ __global__ void __launch_bounds__(256) subtree_push_kernel(P2PBuild pb, uint64_t
   {
     const uint4* src = reinterpret_cast<const uint4*>(pb.nodes[me] + node_first);
     const uint64_t units = node_cnt * (sizeof(WNode) / sizeof(uint4));
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(src);
     for (uint64_t i = tid; i < units; i += nthr) {
+      // slots the build never writes (about half of the padded layout) hold the default leaf on every rank already
+      if (words[(i >> 2) * 16 + 11] & WN_UNUSED) continue;  // WNode::b
       const uint4 v = src[i];
       for (int p = 0; p < pb.world; ++p)
         if (p != me) reinterpret_cast<uint4*>(pb.nodes[p] + node_first)[i] = v;

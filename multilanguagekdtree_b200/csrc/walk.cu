@@ -46,16 +46,18 @@ static void walk_range(const Ctx* c, uint32_t* begin, uint32_t* end) {
 // shard (the tree order moves little from step to step).  Production kernel only, and only while the node records
 // and tree-ordered particles (~66 B per particle) fit the 126 MB L2: the index order is also the spatial order, so
 // the ~3500 groups in flight share their near field; with the cost order they are scattered over the whole domain,
-// which costs nothing when the tree is L2-resident (measured at N = 125k and 1M) and loses where it is not (N = 10M
-// streams the tree from HBM: 20.69 ms in index order, 20.99 ms heaviest first, profiles/r02_ab_walk_lpt_10M.txt) —
-// there the launch stays in index order.  KDNB_WALK_LPT=0 disables, =1 forces it at every size.
+// which costs nothing when the tree is L2-resident (measured at N = 125k and 1M).  Where it is not, what counts is the
+// length of the launch: one GPU walking all of N = 10M loses (20.69 ms in index order, 20.99 ms heaviest first,
+// profiles/r02_ab_walk_lpt_10M.txt), a 1/8 shard of the same tree wins (2.69 -> 2.56 ms on 8 GPUs,
+// profiles/r02_scale_8gpu.txt) because the end of the launch it shortens is a larger part of it.  So: heaviest first
+// while this rank walks at most 2M slots.  KDNB_WALK_LPT=0 disables, =1 forces it at every size.
 static bool walk_uses_order(const Ctx* c, uint32_t begin, uint32_t end) {
   static const int lpt_mode = [] {
     const char* s = getenv("KDNB_WALK_LPT");
     return s ? (atoi(s) != 0 ? 1 : 0) : -1;
   }();
   constexpr uint64_t LPT_MAX_N = 1ull << 21;
-  const bool lpt = lpt_mode == 1 || (lpt_mode < 0 && c->n <= LPT_MAX_N);
+  const bool lpt = lpt_mode == 1 || (lpt_mode < 0 && (uint64_t)(end - begin) <= LPT_MAX_N);
   const bool production = !(c->flags & (KDNB_FLAG_WALK_COUNTS | KDNB_FLAG_EXACT_MATH));
   return production && lpt && end > begin;
 }
