@@ -110,7 +110,9 @@ void kdnb_destroy(kdnb_ctx* ctx);
 const char* kdnb_last_error(const kdnb_ctx* ctx); /* ctx may be NULL (creation errors) */
 int kdnb_version(void);
 
-/* ---- state: `bodies: &mut Vec<Particle>` (array_kd_tree.rs:623).  AoS in, AoS out, original order kept */
+/* ---- state: `bodies: &mut Vec<Particle>` (array_kd_tree.rs:623).  AoS in, AoS out, original order kept.
+ * Uploads enqueue their host-to-device copy and return: a page-locked source (kdnb_host_alloc) must stay untouched until
+ * kdnb_synchronize or a download returns (pageable memory is staged by the driver before the call returns). */
 int kdnb_upload_particles(kdnb_ctx* ctx, const kdnb_particle* aos, uint64_t count);
 int kdnb_download_particles(kdnb_ctx* ctx, kdnb_particle* out, uint64_t capacity);
 uint64_t kdnb_particle_count(const kdnb_ctx* ctx);

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage (under gpurun, one GPU): bash tools_ab.sh <tag> "<N> <steps>" ... -- "VAR=val VAR2=val" ...
+# usage (under gpurun, one GPU): bash tools/ab.sh <tag> "<N> <steps>" ... -- "VAR=val VAR2=val" ...
 # A/B timing of build-time knobs: for every size and every environment set, one bench line (--no-cpu) reduced to
 # value, ms/step and the stage times.  "-" stands for the default environment.  Output: gpurun_out/ab_<tag>.txt
 TAG=$1; shift
