@@ -25,6 +25,12 @@ for kind in ("cluster", "pairs"):
     with kd.KDTreeSim() as sim:
         sim.upload(parts); sim.build_tree(); sim.calc_accel(); sim.simple_sim(1e-5, 5); out = sim.download()
     assert np.isfinite(out["p"]).all()
+# the Sequential crate's SIMD particle surface and a profiled context (event-record nodes in the step graph)
+from multilanguagekdtree_b200 import simd_kd_tree, simd_particle
+b = simd_particle.circular_orbits(4000, seed=2)
+simd_kd_tree.simple_sim(b, 1e-3, 4)
+with kd.KDTreeSim(flags=kd.FLAG_PROFILE) as sim:
+    sim.upload(kd.circular_orbits(30000, seed=9)); sim.simple_sim(1e-3, 5); sim.stage_ms()
 # stand-alone quickstat_index
 vals = rng.random(300000)
 idx = np.arange(len(vals), dtype=np.uint64)
