@@ -37,6 +37,7 @@ static AccSel acc_sel(const Ctx* c) {
 // (a = 0, exactly what the reference's zeroed vector gives), and downloading them yields zeros.  (Measured: zeroing the
 // gathered 24 bytes in place doubles the kernel's time at N = 10M, a separate memset is a launch and 24 B / particle.)
 __global__ void __launch_bounds__(256) kick_drift_kernel(uint32_t n, double dt, V3 pos, V3 vel,
+                                                         const double* __restrict__ mass,
                                                          const uint32_t* __restrict__ rank, AccSel sel, bool use_acc,
                                                          PosM* __restrict__ pm, uint64_t* __restrict__ ss) {
   pdl_sync();
@@ -51,6 +52,8 @@ __global__ void __launch_bounds__(256) kick_drift_kernel(uint32_t n, double dt, 
     const uint64_t j = rank[i];
     const double u0 = vel.p[0][i], u1 = vel.p[1][i], u2 = vel.p[2][i];
     const double p0 = pos.p[0][i], p1 = pos.p[1][i], p2 = pos.p[2][i];
+    const double mi = mass[i];  // (8 bytes read so that the mirror record below is written whole: a 24-of-32-byte
+                                // write makes the L2 fetch the sector first)
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     if (use_acc) a0 = acc_t[3 * j + 0], a1 = acc_t[3 * j + 1], a2 = acc_t[3 * j + 2];
     const double v0 = __dadd_rn(u0, __dmul_rn(dt, a0));  // b.v[k] += dt * a[k]   (:650-652)
@@ -65,9 +68,9 @@ __global__ void __launch_bounds__(256) kick_drift_kernel(uint32_t n, double dt, 
     pos.p[0][i] = x;
     pos.p[1][i] = y;
     pos.p[2][i] = z;
-    pm[i].x = x;  // AoS mirror read by the next build
-    pm[i].y = y;
-    pm[i].z = z;
+    PosM rec;  // AoS mirror read by the next build
+    rec.x = x, rec.y = y, rec.z = z, rec.m = mi;
+    pm[i] = rec;
   }
   accumulate_extent(x, y, z, valid, 2u, ss, sm);  // (2: the masses did not change, sort_prep keeps what the upload found)
 }
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(256) kick_drift_kernel(uint32_t n, double dt, 
 int kick_drift(Ctx* c, double dt) {
   const uint32_t n = (uint32_t)c->n;
   V3 pos = {{c->pos[0], c->pos[1], c->pos[2]}}, vel = {{c->vel[0], c->vel[1], c->vel[2]}};
-  KDNB_LAUNCH(c, kick_drift_kernel, (n + 255) / 256, 256, 0, n, dt, pos, vel, c->rank, acc_sel(c), c->acc_valid, c->pm,
+  KDNB_LAUNCH(c, kick_drift_kernel, (n + 255) / 256, 256, 0, n, dt, pos, vel, c->mass, c->rank, acc_sel(c), c->acc_valid, c->pm,
               c->sort_state);
   KDNB_CHECK_LAUNCH(c);
   c->extent_fresh = true;
