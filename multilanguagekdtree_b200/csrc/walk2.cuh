@@ -102,6 +102,20 @@ __device__ __forceinline__ void interact_exact(double ex, double ey, double ez, 
   }
 }
 
+// KDNB_WALK_CPASYNC (compile-time experiment, -DKDNB_WALK_CPASYNC): leaf particles go from global memory straight into
+// their list slots with cp.async (LDGSTS, 8 bytes per coordinate: the list is SoA in blocks of four) instead of a
+// 32-byte load into registers + four shared-memory stores; the drain waits for the group before it reads the list.
+// Measured (profiles/r02_ab_walk_cpasync.txt, parity green): walk 2.081 -> 2.095 ms at N=1M, 20.28 -> 20.45 ms at N=10M —
+// the kernel is bound by issue slots, its loads were never exposed, and the asynchronous copies no
+// longer overlap the drain that used to run between the load and the stores.  Not the default.
+#ifdef KDNB_WALK_CPASYNC
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
+
 // all lanes stream over the list; lane = particle
 #ifdef KDNB_WALK_AB
 __device__ int w2_dbg;  // development experiments: 1 = skip the drains, 2 = drain every list twice
@@ -109,6 +123,9 @@ __device__ int w2_dbg;  // development experiments: 1 = skip the drains, 2 = dra
 template <bool EXACT, bool FLATZ>
 __device__ __forceinline__ void drain2(W2Smem& S, int cnt, int lane, double px, double py, double pz, double& ax,
                                        double& ay, double& az) {
+#ifdef KDNB_WALK_CPASYNC
+  cp_async_wait_all();
+#endif
   __syncwarp();
 #ifdef KDNB_WALK_AB
   const int dbg = w2_dbg;
@@ -394,6 +411,26 @@ __device__ __forceinline__ void walk2_body(W2Smem& S, const WNode* __restrict__ 
         const bool valid = k < L.y && m != 0u;
         const uint32_t bal = __ballot_sync(0xffffffffu, valid);
         const int add = __popc(bal);
+#ifdef KDNB_WALK_CPASYNC
+        if (ln + add > W2_LIST) {
+          drain2<EXACT, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
+          work += (uint32_t)ln;
+          ln = 0;
+        }
+        if (valid) {
+          const int i = ln + __popc(bal & lt);
+          W2Blk& B = S.blk[i >> 2];
+          const int s = i & 3;
+          const PosM* g = posm + j;
+          cp_async8(&B.x[s], &g->x);
+          cp_async8(&B.y[s], &g->y);
+          cp_async8(&B.m[s], &g->m);
+          if (!FLATZ) cp_async8(&S.lz[i], &g->z);
+          B.mask[s] = m;
+          if (EXACT) B.flag[s] = 1u;
+        }
+        ln += add;
+#else
         PosM qv;
         if (valid) qv = posm[j];
         if (ln + add > W2_LIST) {
@@ -403,6 +440,7 @@ __device__ __forceinline__ void walk2_body(W2Smem& S, const WNode* __restrict__ 
         }
         if (valid) list_put<EXACT, FLATZ>(S, ln + __popc(bal & lt), qv.x, qv.y, qv.z, qv.m, m, 1u);
         ln += add;
+#endif
         if (COUNTS) {
           for (int s = 0; s < 32; ++s) {
             const uint32_t ms = __shfl_sync(0xffffffffu, valid ? m : 0u, s);
