@@ -158,6 +158,12 @@ uint64_t kdnb_node_count(const kdnb_ctx* ctx); /* allocate_node_vec(count).len()
  * ranges, tree-ordered accelerations exchanged with one ncclAllGather per step. */
 /* pure: the tree-slot range [begin, end) rank `rank` of `world_size` walks for `count` particles (warp-aligned shards) */
 int kdnb_shard_range(uint64_t count, int rank, int world_size, uint64_t* begin, uint64_t* end);
+/* multi-GPU, sharded tree build: what rank `rank` of a power-of-two `world_size` builds below the top log2(world_size)
+ * levels — the subtree of its level-log2(world) segment: tree slots [first_slot, first_slot + slots) and node indices
+ * [first_node, first_node + nodes) in the given layout (closed forms of `count`: array_kd_tree.rs:560, :566-581,
+ * :120-126).  Pure; KDNB_E_INVALID when world_size is not a power of two. */
+int kdnb_build_shard_plan(uint64_t count, uint32_t max_parts, int layout, int rank, int world_size, uint64_t* first_slot,
+                          uint64_t* slots, uint64_t* first_node, uint64_t* nodes);
 int kdnb_comm_unique_id(void* id_out_128_bytes);
 int kdnb_comm_init(kdnb_ctx* ctx, const void* id_128_bytes, int rank, int world_size);
 

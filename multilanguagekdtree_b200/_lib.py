@@ -32,7 +32,7 @@ SYMBOLS = [
     "kdnb_shard_range", "kdnb_host_shard_range", "kdnb_upload_particles_sharded",
     "kdnb_download_particles_sharded", "kdnb_simple_sim_bodies_sharded", "kdnb_comm_unique_id", "kdnb_comm_init", "kdnb_stage_ms", "kdnb_stage_reset", "kdnb_launch_count",
     "kdnb_measure_fp64_peak", "kdnb_flush_l2", "kdnb_device_ms", "kdnb_host_alloc", "kdnb_host_free",
-    "kdnb_quickstat_index", "kdnb_upload_particles_simd", "kdnb_download_particles_simd", "kdnb_simple_sim_bodies_simd",
+    "kdnb_quickstat_index", "kdnb_upload_particles_simd", "kdnb_download_particles_simd", "kdnb_simple_sim_bodies_simd", "kdnb_build_shard_plan",
 ]
 
 
@@ -103,6 +103,8 @@ def load() -> C.CDLL:
     L.kdnb_host_free.argtypes = [vp]
     L.kdnb_quickstat_index.argtypes = [vp, vp, u64, vp, u64, u64, vp]
     L.kdnb_quickstat_index.restype = i32
+    L.kdnb_build_shard_plan.argtypes = [u64, u32, i32, i32, i32, vp, vp, vp, vp]
+    L.kdnb_build_shard_plan.restype = i32
     L.kdnb_upload_particles_simd.argtypes = [vp, vp, u64]
     L.kdnb_download_particles_simd.argtypes = [vp, vp, u64]
     L.kdnb_simple_sim_bodies_simd.argtypes = [vp, vp, u64, f64, i64]

@@ -43,6 +43,16 @@ def shard_range(count: int, rank: int, world: int):
     return int(b.value), int(e.value)
 
 
+def build_shard_plan(count: int, rank: int, world: int, max_parts: int = MAX_PARTS, layout: int = LAYOUT_PADDED):
+    """What rank `rank` builds in a sharded tree build: (first_slot, slots, first_node, nodes) of its subtree below the top
+    log2(world) levels (kdnb_build_shard_plan; pure, needs no GPU)."""
+    v = [C.c_uint64(0) for _ in range(4)]
+    rc = _lib.load().kdnb_build_shard_plan(count, max_parts, layout, rank, world, *[C.byref(x) for x in v])
+    if rc != 0:
+        raise KdnbError(f"kdnb_build_shard_plan rc={rc}")
+    return tuple(int(x.value) for x in v)
+
+
 def host_shard_range(total: int, rank: int, world: int):
     """Slice [first, first+count) of the global particle array that rank `rank` keeps on the host (kdnb_host_shard_range)."""
     f, n = C.c_uint64(0), C.c_uint64(0)

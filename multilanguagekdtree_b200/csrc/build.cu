@@ -656,7 +656,7 @@ void init_unused_nodes(Ctx* c) {
 
 // level-k segment `seg` of the tree over n particles: first slot, length and node index (splits are always at len / 2,
 // :560, and a left subtree occupies the node indices right after its parent, :566-581 / :120-126), host side
-static void subtree_of(uint64_t n, uint32_t mp, int layout, int k, uint32_t seg, uint64_t* a, uint64_t* len, uint64_t* node) {
+void subtree_of(uint64_t n, uint32_t mp, int layout, int k, uint32_t seg, uint64_t* a, uint64_t* len, uint64_t* node) {
   uint64_t fa = 0, fl = n, fn = 0;
   for (int lev = k - 1; lev >= 0; --lev) {
     const uint64_t left = fl / 2;

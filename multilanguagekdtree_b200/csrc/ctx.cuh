@@ -157,6 +157,7 @@ int sort_lists(Ctx* c);
 int build_tree(Ctx* c);
 int export_tree(Ctx* c, kdnb_node* dev_out);
 void init_unused_nodes(Ctx* c);
+void subtree_of(uint64_t n, uint32_t mp, int layout, int k, uint32_t seg, uint64_t* a, uint64_t* len, uint64_t* node);
 // walk.cu
 int walk(Ctx* c);
 void walk_order_fork(Ctx* c);

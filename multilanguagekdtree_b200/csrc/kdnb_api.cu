@@ -860,6 +860,20 @@ int kdnb_shard_range(uint64_t count, int rank, int world_size, uint64_t* begin, 
   return 0;
 }
 
+int kdnb_build_shard_plan(uint64_t count, uint32_t max_parts, int layout, int rank, int world_size, uint64_t* first_slot,
+                          uint64_t* slots, uint64_t* first_node, uint64_t* nodes) {
+  if (world_size < 1 || rank < 0 || rank >= world_size || max_parts < 4 || max_parts > 32 || !first_slot || !slots || !first_node || !nodes)
+    return KDNB_E_INVALID;
+  if (layout != KDNB_LAYOUT_PADDED && layout != KDNB_LAYOUT_DENSE) return KDNB_E_INVALID;
+  int k = 0;
+  while ((1 << k) < world_size) ++k;
+  if ((1 << k) != world_size) return KDNB_E_INVALID;
+  uint64_t a = 0, len = 0, node = 0;
+  subtree_of(count, max_parts, layout, k, (uint32_t)rank, &a, &len, &node);
+  *first_slot = a, *slots = len, *first_node = node, *nodes = subtree_nodes(len, max_parts, layout);
+  return 0;
+}
+
 int kdnb_comm_unique_id(void* id_out) {
   std::string why;
   if (!id_out || !load_nccl(&why)) {

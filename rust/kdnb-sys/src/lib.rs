@@ -93,6 +93,7 @@ extern "C" {
     pub fn kdnb_upload_particles_sharded(ctx: *mut kdnb_ctx, shard: *const kdnb_particle, total: u64) -> c_int;
     pub fn kdnb_download_particles_sharded(ctx: *mut kdnb_ctx, shard_out: *mut kdnb_particle) -> c_int;
     pub fn kdnb_simple_sim_bodies_sharded(ctx: *mut kdnb_ctx, shard: *mut kdnb_particle, total: u64, dt: c_double, steps: i64) -> c_int;
+    pub fn kdnb_build_shard_plan(count: u64, max_parts: u32, layout: c_int, rank: c_int, world_size: c_int, first_slot: *mut u64, slots: *mut u64, first_node: *mut u64, nodes: *mut u64) -> c_int;
     pub fn kdnb_comm_unique_id(id_out_128_bytes: *mut c_void) -> c_int;
     pub fn kdnb_comm_init(ctx: *mut kdnb_ctx, id_128_bytes: *const c_void, rank: c_int, world_size: c_int) -> c_int;
     pub fn kdnb_stage_ms(ctx: *mut kdnb_ctx, ms_out: *mut c_double, steps_out: *mut u64) -> c_int;

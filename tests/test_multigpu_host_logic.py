@@ -41,6 +41,13 @@ def _worker(rank, world, port, n, out):
         dist.all_gather(gathered, mine)
         got = torch.cat(gathered)[:n]
         assert torch.equal(got, full)
+        # the sharded tree build: every rank's subtree plan (slots and node indices), gathered, tiles the tree
+        plans = [None] * world
+        dist.all_gather_object(plans, kd.build_shard_plan(n, rank, world))
+        assert plans[0][0] == 0 and sum(p[1] for p in plans) == n
+        assert all(plans[i][0] + plans[i][1] == plans[i + 1][0] for i in range(world - 1))
+        assert all(plans[i][2] + plans[i][3] <= plans[i + 1][2] for i in range(world - 1))     # node ranges disjoint, in order
+        assert plans[-1][2] + plans[-1][3] <= kd.nodes_needed_for_particles(n) or n <= 8
         # max-over-ranks timing reduction used by bench.py
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -76,3 +83,33 @@ def test_shard_range_pure():
             assert covered == n
     with pytest.raises(kd.KdnbError):
         kd.shard_range(10, 2, 2)
+
+
+def test_build_shard_plan_matches_the_oracle_tree():
+    """The closed forms behind the sharded build (kdnb_build_shard_plan) against an actual tree of the CPU oracle: the
+    level-k segments' slot ranges and node indices, padded and dense layouts, several sizes and world sizes."""
+    from oracle.okd import LAYOUT_DENSE as O_DENSE, LAYOUT_PADDED as O_PADDED, Oracle
+    orc = Oracle()
+    for n in (4097, 20001, 33333):
+        parts = orc.circular_orbits(n - 1, seed=n)
+        for layout, olayout in ((kd.LAYOUT_PADDED, O_PADDED), (kd.LAYOUT_DENSE, O_DENSE)):
+            nodes, idx, _ = orc.build_tree_canonical(parts, layout=olayout)
+            for world in (2, 4, 8):
+                k = world.bit_length() - 1
+                # walk the oracle's tree down k levels: (node, first slot, length) of every level-k segment
+                segs = [(0, 0, n)]
+                for _ in range(k):
+                    nxt = []
+                    for node, a, ln in segs:
+                        assert nodes["is_internal"][node]
+                        left, right = int(nodes["left"][node]), int(nodes["right"][node])
+                        nxt += [(left, a, ln // 2), (right, a + ln // 2, ln - ln // 2)]
+                    segs = nxt
+                for r, (node, a, ln) in enumerate(segs):
+                    first_slot, slots, first_node, cnt = kd.build_shard_plan(n, r, world, layout=layout)
+                    assert (first_slot, slots, first_node) == (a, ln, node), (n, layout, world, r)
+                    nxt_node = segs[r + 1][0] if r + 1 < len(segs) else None
+                    if nxt_node is not None:
+                        assert first_node + cnt <= nxt_node
+    with pytest.raises(kd.KdnbError):
+        kd.build_shard_plan(1000, 0, 3)
