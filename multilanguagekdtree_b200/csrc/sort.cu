@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(256) sort_fetch_kernel(P2PBuild pb, uint32_t* 
 constexpr int FIX_CAP = 32;
 __global__ void __launch_bounds__(256) sort_fixup(Pos3 pos, const uint32_t* __restrict__ keys, uint32_t* __restrict__ lists,
                                                   uint32_t n, const uint32_t* __restrict__ flat,
-                                                  uint64_t* __restrict__ ss) {
+                                                  uint64_t* __restrict__ ss, int kshift) {
   pdl_sync();
   const int d = blockIdx.y;
   if (flat[d] || ss[SS_NEED64]) return;
@@ -399,12 +399,13 @@ __global__ void __launch_bounds__(256) sort_fixup(Pos3 pos, const uint32_t* __re
   const uint32_t* key = keys + (uint64_t)d * n;
   uint32_t* lst = lists + (uint64_t)d * n;
   const double* x = pos.p[d];
-  const uint32_t k = key[i];
-  const bool start = i == 0 || key[i - 1] != k;
+  // (kshift > 0: the passes skipped the lowest digits — a run is a stretch of equal key >> kshift)
+  const uint32_t k = key[i] >> kshift;
+  const bool start = i == 0 || (key[i - 1] >> kshift) != k;
   if (start) {
-    if (i + 1 >= n || key[i + 1] != k) return;  // singleton
+    if (i + 1 >= n || (key[i + 1] >> kshift) != k) return;  // singleton
     uint32_t len = 2;
-    while (len <= FIX_CAP && i + len < n && key[i + len] == k) ++len;
+    while (len <= FIX_CAP && i + len < n && (key[i + len] >> kshift) == k) ++len;
     if (len > FIX_CAP) return;  // long run: verified pair by pair by its members
     if (len == 2) {
       const uint32_t a = lst[i], b = lst[i + 1];
@@ -434,8 +435,8 @@ __global__ void __launch_bounds__(256) sort_fixup(Pos3 pos, const uint32_t* __re
     if (f64_key(x[a]) <= f64_key(x[b])) return;
     // out of order (or caught mid-update of a short run, which its start thread finishes): long run?
     uint32_t s = i, e = i + 1;
-    while (s > 0 && i - s <= FIX_CAP && key[s - 1] == k) --s;
-    while (e < n && e - s <= FIX_CAP && key[e] == k) ++e;
+    while (s > 0 && i - s <= FIX_CAP && (key[s - 1] >> kshift) == k) --s;
+    while (e < n && e - s <= FIX_CAP && (key[e] >> kshift) == k) ++e;
     if (e - s > FIX_CAP) ss[SS_NEED64] = 1ull;
   }
 }
@@ -456,27 +457,30 @@ __global__ void sort_set_cond(cudaGraphConditionalHandle h, const uint64_t* __re
   cudaGraphSetConditional(h, ss[SS_NEED64] ? 1u : 0u);
 }
 
-// Sorted lists end in c->list[0] (32-bit keys: positions -> buf1 -> buf0 -> buf1 -> buf0; 64-bit keys: 8 passes,
-// same parity).
+// Sorted lists end in c->list[0] whatever the number of passes: the buffers alternate so that the LAST pass writes
+// buffer 0 (four passes: positions -> buf1 -> buf0 -> buf1 -> buf0; three: positions -> buf0 -> buf1 -> buf0).
+// first_pass > 0 skips the lowest digits: the lists are then ordered by key >> (8 * first_pass) only and sort_fixup
+// finishes the (longer) runs of equal truncated keys — see sort_lists().
 template <typename K>
-static void sort_passes(Ctx* c, Pos3 pos, bool gated) {
+static void sort_passes(Ctx* c, Pos3 pos, bool gated, int first_pass = 0) {
   const uint32_t n = (uint32_t)c->n;
   const uint32_t nt = c->ntiles;
   const int passes = (int)sizeof(K);
   dim3 gt(nt, 3), gs(256, 3);
   K* kb[2] = {reinterpret_cast<K*>(c->keys[0]), reinterpret_cast<K*>(c->keys[1])};
   const uint64_t* ss = c->sort_state;
-  for (int pass = 0; pass < passes; ++pass) {
+  for (int pass = first_pass; pass < passes; ++pass) {
     const int shift = 8 * pass;
-    const int src = (pass & 1) ? 1 : 0, dst = src ^ 1;  // pass 0 reads positions, writes buf1
-    if (pass == 0) {
+    const int dst = ((passes - 1 - pass) & 1) ? 1 : 0, src = dst ^ 1;  // the last pass writes buffer 0
+    const bool first = pass == first_pass;
+    if (first) {
       KDNB_LAUNCH(c, (sort_upsweep<true, K>), gt, SORT_THREADS, 0, pos, nullptr, n, shift, nt, c->hist, c->dmask, ss, gated);
     } else {
       KDNB_LAUNCH(c, (sort_upsweep<false, K>), gt, SORT_THREADS, 0, pos, kb[src], n, shift, nt, c->hist, c->dmask, ss, gated);
     }
     KDNB_LAUNCH(c, sort_scan_rows, gs, 256, 0, c->hist, nt, c->digit_tot, c->dmask, ss, gated);
-    if (pass == 0) {
-      KDNB_LAUNCH(c, (sort_downsweep<true, false, K>), gt, SORT_THREADS, 0, pos, nullptr, nullptr, kb[1], c->list[1], n,
+    if (first) {
+      KDNB_LAUNCH(c, (sort_downsweep<true, false, K>), gt, SORT_THREADS, 0, pos, nullptr, nullptr, kb[dst], c->list[dst], n,
                   shift, nt, c->hist, c->digit_tot, c->dmask, ss, gated);
     } else if (pass == passes - 1 && sizeof(K) == 8) {  // (the 32-bit keys of the last pass are read by sort_fixup)
       KDNB_LAUNCH(c, (sort_downsweep<false, true, K>), gt, SORT_THREADS, 0, pos, kb[src], c->list[src], kb[dst],
@@ -566,9 +570,19 @@ int sort_lists(Ctx* c) {
   if (only64) {
     sort_passes<uint64_t>(c, pos, false);
   } else {
-    sort_passes<uint32_t>(c, pos, false);
+    // Up to 4M particles THREE passes: the lowest digit is skipped, the lists come out ordered by the top 24 bits of
+    // the scaled key and sort_fixup orders the runs of equal 24-bit keys (16.7M bins: a few per cent of the particles
+    // share one at N = 1M; a run longer than 32 that is out of order still raises need64, i.e. only an input with
+    // ~500 times the average density inside a 2^-24 slice of its extent falls back).  One radix pass fewer: -3 launches,
+    // measured in profiles/r02_ab_sort_3pass.txt.  KDNB_SORT_PASSES=4 restores the four passes.
+    static const bool four = [] {
+      const char* e = getenv("KDNB_SORT_PASSES");
+      return e && atoi(e) == 4;
+    }();
+    const int skip = (!four && c->n <= (4ull << 20)) ? 1 : 0;
+    sort_passes<uint32_t>(c, pos, false, skip);
     KDNB_LAUNCH(c, sort_fixup, dim3((n + 255) / 256, 3), 256, 0, pos, reinterpret_cast<const uint32_t*>(c->keys[0]),
-                c->list[0], n, c->dmask, c->sort_state);
+                c->list[0], n, c->dmask, c->sort_state, 8 * skip);
     // the 64-bit passes run only when need64 was raised: decided by the host between plain launches (one stream
     // synchronisation), by a conditional node inside a captured step, by the kernels themselves otherwise
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
