@@ -634,6 +634,31 @@ def test_graph_replay_equals_plain_launches(orc):
         assert a.download().tobytes() == b.download().tobytes()
 
 
+def test_simple_sim_zero_steps_and_staged_semantics(orc):
+    """`for _ in 0..steps` (array_kd_tree.rs:632): steps <= 0 never advances the state — also on the call that would
+    capture the step graph (third consecutive call).  And the reference's `a = 0` after a kick (:659-661): a second kick
+    without a walk in between applies zero accelerations, and downloading consumed accelerations gives zeros."""
+    parts = orc.circular_orbits(5000, seed=8)
+    with kd.KDTreeSim() as sim:
+        sim.upload(parts)
+        for steps in (0, -1, 0, 0, -5):
+            sim.simple_sim(1e-3, steps)
+        assert sim.download().tobytes() == parts.tobytes()
+        sim.build_tree()
+        assert not sim.accel().any()                 # before the first calc_accel
+        sim.calc_accel()
+        acc = sim.accel()
+        assert acc.any()
+        sim.kick_drift(1e-3)
+        after1 = sim.download()
+        assert not sim.accel().any()                 # consumed: a = 0
+        sim.kick_drift(1e-3)                         # no walk in between: v unchanged, p += dt * v
+        after2 = sim.download()
+    v1 = parts["v"] + 1e-3 * acc
+    assert np.array_equal(after1["v"], v1) and np.array_equal(after2["v"], v1)
+    assert np.array_equal(after2["p"], after1["p"] + 1e-3 * v1)
+
+
 @pytest.mark.parametrize("kind", ["two_scales", "pairs"])
 def test_graph_replay_with_64_bit_sort_fallback(orc, kind):
     """Inside a replayed step the 64-bit sort passes sit in a conditional graph node; inputs that need them (and
