@@ -242,7 +242,9 @@ def measure(kd, L, torch, dist, local, rank, world, n, K, W, with_counts=True):
     simp.upload(host)
     simp.simple_sim(DT, W)
     simp.stage_reset()
+    simp.stopwatch_begin()
     simp.simple_sim(DT, K)
+    prof_ms = simp.stopwatch_end()
     stage, nsteps = simp.stage_ms()
     simp.close()
     value = (n + 1) * K / (ms * 1e-3)
@@ -277,6 +279,9 @@ def measure(kd, L, torch, dist, local, rank, world, n, K, W, with_counts=True):
     rec = {
         "value": value, "ms_per_step": ms / K, "steps": K, "warmup": W, "gpu_launches": int(launches),
         "stage_ms_per_step": {k: stage[k] / max(1, nsteps) for k in ("build", "walk", "kick", "exchange")},
+        # the context the stage times come from: its own K steps, device-timed (five event-record nodes per step and a
+        # host wait after every step, so slightly above ms_per_step; the stage times add up to at most this)
+        "stage_context_ms_per_step": prof_ms / K,
         "e2e": {"value": (n + 1) * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb,
                 "note": "K calls of kdnb_simple_sim_bodies[_sharded](host, dt, 1): pinned-host upload + one step + download per call; bytes are the sum over ranks (each rank moves its 1/N host shard over PCIe, NVLink all-gather for the rest)"},
         "e2e_amortized": {"value": (n + 1) * K / e2e_amort_s, "unit": UNIT, "note": "one call simple_sim(bodies, dt, K) with host buffers"},
@@ -416,6 +421,7 @@ def run_kdnb(args) -> None:
                 "timer": "CUDA events on the library's stream around K steps (step replayed as a CUDA graph), max over ranks; stage_ms from a second context in the same mode (graph replay with event-record nodes at the stage boundaries)",
             },
             "stage_ms_per_step": top["stage_ms_per_step"],
+            "stage_context_ms_per_step": top["stage_context_ms_per_step"],
             "roofline": top.get("roofline"),
             "roofline_hbm": hbm(n, top),
             "e2e": top["e2e"], "e2e_amortized": top["e2e_amortized"],
