@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage (under gpurun --gpus 8): bash tools/r02_scale.sh <tag>
 # The scaling lines the driver takes at round end (bench.py at N = 8, 4, 2: top-level 1M line + n10m sub-record + parity),
-# the heaviest-first order at the 10M x 8 shard size, and the BASELINE configs[4] sweep (N = 100M, theta x MAX_PARTS).
+# the split sort forced at 1M x 8 (default: from 2M particles), and the BASELINE configs[4] sweep (N = 100M, theta x MAX_PARTS).
 TAG=${1:-r02}
 mkdir -p gpurun_out
 t0=$SECONDS
@@ -17,8 +17,8 @@ for g in 8 4 2; do
   run $g 2951$g bench.py --gpus $g --steps 10 --warmup 3 > gpurun_out/scale_${TAG}_n$g.log 2>&1
   echo "bench N=$g rc=$? $((SECONDS - t0)) s"; summ gpurun_out/scale_${TAG}_n$g.log
 done
-KDNB_WALK_LPT=1 run 8 29520 bench.py --gpus 8 --steps 10 --warmup 3 --number 10000000 --no-10m > gpurun_out/scale_${TAG}_lpt10M.log 2>&1
-echo "LPT=1 10M x 8 rc=$? $((SECONDS - t0)) s"; summ gpurun_out/scale_${TAG}_lpt10M.log
+KDNB_SORT_SPLIT=1 run 8 29520 bench.py --gpus 8 --steps 10 --warmup 3 --no-10m > gpurun_out/scale_${TAG}_split1M.log 2>&1
+echo "KDNB_SORT_SPLIT=1 at 1M x 8 rc=$? $((SECONDS - t0)) s"; summ gpurun_out/scale_${TAG}_split1M.log
 run 8 29540 benchmarks/sweep_100m.py --steps 2 > gpurun_out/sweep_100m_${TAG}.log 2>&1
 echo "sweep rc=$? $((SECONDS - t0)) s"; grep '^{' gpurun_out/sweep_100m_${TAG}.log | cut -c1-400
 tail -3 gpurun_out/sweep_100m_${TAG}.log | cut -c1-300
