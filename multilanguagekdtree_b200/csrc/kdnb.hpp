@@ -141,3 +141,46 @@ inline void simple_sim(std::vector<Particle>& bodies, double dt, int64_t steps) 
 }
 
 }  // namespace array_kd_tree
+
+// ---- the Sequential crate's SIMD surface (Sequential/RustVersion/src/simd_particle.rs, simd_kd_tree.rs)
+namespace simd_particle {
+
+using Particle = kdnb_particle_simd;  // simd_particle.rs:3-8: { p: f64x4, v: f64x4, r, m }, 96 bytes, lane 3 = 0
+
+// simd_particle.rs:10-27
+inline std::vector<Particle> two_bodies() {
+  std::vector<Particle> b(2);
+  b[0] = Particle{{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}, 1.0, 1.0, {0.0, 0.0}};
+  b[1] = Particle{{1.0, 0.0, 0.0, 0.0}, {0.0, 1.0, 0.0, 0.0}, 1e-4, 1e-20, {0.0, 0.0}};
+  return b;
+}
+
+// simd_particle.rs:29-55 — n+1 particles, angles u * TAU (the array version uses 6.28); seeded splitmix64 stream
+inline std::vector<Particle> circular_orbits(size_t n, uint64_t seed = 12345) {
+  std::vector<Particle> buf;
+  buf.reserve(n + 1);
+  buf.push_back(Particle{{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}, 0.00465047, 1.0, {0.0, 0.0}});
+  uint64_t st = seed;
+  for (size_t i = 0; i < n; ++i) {
+    const double d = 0.1 + ((double)i * 5.0 / (double)n);
+    const double v = std::sqrt(1.0 / d);
+    const double theta = (double)(array_particle::splitmix64(st) >> 11) * 0x1.0p-53 * 6.283185307179586;
+    buf.push_back(Particle{{d * std::cos(theta), d * std::sin(theta), 0.0, 0.0},
+                           {-v * std::sin(theta), v * std::cos(theta), 0.0, 0.0}, 1e-7, 1e-14, {0.0, 0.0}});
+  }
+  return buf;
+}
+
+}  // namespace simd_particle
+
+namespace simd_kd_tree {
+
+constexpr size_t MAX_PARTS = 7;  // simd_kd_tree.rs:9
+
+// simd_kd_tree.rs:169-202 (dense `build_tree` layout, :49-138)
+inline void simple_sim(std::vector<simd_particle::Particle>& bodies, double dt, int64_t steps) {
+  array_kd_tree::Context c(0, KDNB_LAYOUT_DENSE, (uint32_t)MAX_PARTS);
+  c.check(kdnb_simple_sim_bodies_simd(c.get(), bodies.data(), bodies.size(), dt, steps), "kdnb_simple_sim_bodies_simd");
+}
+
+}  // namespace simd_kd_tree

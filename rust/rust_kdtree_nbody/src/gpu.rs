@@ -90,6 +90,12 @@ impl Context {
         }
     }
 
+    /// The Sequential crate's SIMD surface: `simple_sim` on 96-byte f64x4 records (simd_kd_tree.rs:169-202).
+    pub fn simple_sim_bodies_simd(&mut self, bodies: &mut [sys::kdnb_particle_simd], dt: f64, steps: i64) -> Result<()> {
+        let rc = unsafe { sys::kdnb_simple_sim_bodies_simd(self.raw, bodies.as_mut_ptr(), bodies.len() as u64, dt, steps) };
+        self.check(rc)
+    }
+
     pub fn particle_count(&self) -> usize {
         unsafe { sys::kdnb_particle_count(self.raw) as usize }
     }

@@ -5,3 +5,5 @@ pub mod array_kd_tree;
 pub mod array_particle;
 pub mod gpu;
 pub mod quickstat;
+pub mod simd_kd_tree;
+pub mod simd_particle;
