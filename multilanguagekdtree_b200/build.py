@@ -26,13 +26,13 @@ def _newer(target: str, sources: list[str]) -> bool:
     if not os.path.exists(target):
         return False
     t = os.path.getmtime(target)
-    return all(os.path.getmtime(s) <= t for s in sources)
+    return all(os.path.exists(s) and os.path.getmtime(s) <= t for s in sources)  # (a listed file that is gone: rebuild)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, f) for f in CU]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("common.cuh", "ctx.cuh", "walk2.cuh", "walk_legacy.cuh")] + [os.path.join(HERE, "..", "include", "kdnb.h")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("common.cuh", "ctx.cuh", "walk2.cuh")] + [os.path.join(HERE, "..", "include", "kdnb.h")]
     extra = os.environ.get("KDNB_NVCC_EXTRA", "").split()   # compile-time experiment knobs, e.g. -DKDNB_BOT_CAP=1024
     if force or extra or not _newer(LIB, deps):
         cmd = [nvcc, *NVCC_FLAGS, *extra, "-shared", "-o", LIB, *srcs, "-ldl"]

@@ -135,3 +135,17 @@ def test_rust_host_crate_mirrors_the_reference_api_and_only_calls_declared_symbo
         assert item in part, item
     main = files["rust/rust_kdtree_nbody/src/main.rs"]
     assert '"--number"' in main and '"--steps"' in main and "1e-3" in main
+
+
+def test_incremental_build_entry_point_with_the_library_already_built():
+    """__graft_entry__.build() on a tree whose libkdnb.so exists takes the up-to-date check: every dependency it lists
+    must exist (a stale name made the check raise instead of answering), and the call must be a no-op that succeeds."""
+    from multilanguagekdtree_b200 import build as kbuild
+    assert os.path.exists(kbuild.LIB)
+    src = open(kbuild.__file__).read()
+    for name in re.findall(r'"([A-Za-z0-9_]+\.(?:cu|cuh|hpp|cpp|h))"', src):
+        cands = [os.path.join(kbuild.CSRC, name), os.path.join(kbuild.HERE, "..", "include", name)]
+        assert any(os.path.exists(c) for c in cands), f"build.py names {name}, which does not exist"
+    before = os.path.getmtime(kbuild.LIB)
+    assert kbuild.build(force=False) == kbuild.LIB
+    assert os.path.getmtime(kbuild.LIB) == before
