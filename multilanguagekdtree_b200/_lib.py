@@ -7,7 +7,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libkdnb.so")
+# KDNB_LIB: another build of the same library (compile-time A/B variants, tools/ab.sh); default = the in-tree build
+LIB_PATH = os.environ.get("KDNB_LIB") or os.path.join(HERE, "libkdnb.so")
 
 # mirrors kdnb_particle == `pub struct Particle` (Parallel/RustVersion/src/array_particle.rs:3-8)
 PARTICLE = np.dtype([("p", "<f8", (3,)), ("v", "<f8", (3,)), ("r", "<f8"), ("m", "<f8")], align=True)
