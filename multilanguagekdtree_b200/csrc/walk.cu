@@ -128,8 +128,14 @@ static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
     // 2.219 ms at 31251; profiles/r01_ab_walk_minb.txt) — the ~0.12 ms a launch takes beyond its issue-slot work is
     // not a matter of waves; nor of node / leaf load latency: prefetching the right child at push time and a leaf's
     // particles at classification made every size ~1 % slower (profiles/r01_ab_walk_prefetch.txt).
+#ifdef KDNB_WALK_AB  // development experiment: KDNB_WALK_PAD=<bytes> of unused dynamic shared memory limits the CTAs per SM
+    static const int pad = [] { const char* s = getenv("KDNB_WALK_PAD"); return s ? atoi(s) : 0; }();
+#else
+    constexpr int pad = 0;
+#endif
     if (minb == 32) KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 32>), grid, 32, 0, KDNB_WALK_ARGS);
-    else KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 24>), grid, 32, 0, KDNB_WALK_ARGS);
+    else if (minb == 28) KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 28>), grid, 32, 0, KDNB_WALK_ARGS);
+    else KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 24>), grid, 32, pad, KDNB_WALK_ARGS);
   }
 #undef KDNB_WALK_ARGS
 }

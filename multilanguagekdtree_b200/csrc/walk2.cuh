@@ -42,7 +42,10 @@
 
 namespace kdnb {
 
-constexpr int W2_STACK = 320;  // soft capacity: batches shrink as the stack fills
+#ifndef KDNB_W2_STACK
+#define KDNB_W2_STACK 320
+#endif
+constexpr int W2_STACK = KDNB_W2_STACK;  // soft capacity: batches shrink as the stack fills
 constexpr int W2_SLACK = 32;   // depth-first tail when the stack is at capacity (tree depth <= 27 at 1e8 particles)
 constexpr int W2_LIST = 96;    // interaction-list capacity (appends come in groups of <= 32); multiple of 4
 

@@ -14,7 +14,7 @@ for sz in "${SIZES[@]}"; do
   read N K <<< "$sz"
   for envs in "${ENVSETS[@]}"; do
     [ "$envs" = "-" ] && e="" || e="$envs"
-    env $e timeout 200 python bench.py --steps $K --warmup 3 --number $N --no-cpu > gpurun_out/ab_tmp.log 2>&1
+    env $e timeout 200 python bench.py --steps $K --warmup 3 --number $N --no-cpu --no-10m > gpurun_out/ab_tmp.log 2>&1
     grep '^{' gpurun_out/ab_tmp.log | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); s=d['stage_ms_per_step']
