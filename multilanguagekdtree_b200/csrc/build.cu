@@ -252,7 +252,7 @@ static_assert(sizeof(BotTab) == 12, "BotTab");
 #define KDNB_BOT_THREADS 256
 #endif
 constexpr int BOT_THREADS = KDNB_BOT_THREADS;
-constexpr int BOT_IPT = BOT_CAP / BOT_THREADS;
+constexpr int BOT_IPT = (BOT_CAP + BOT_THREADS - 1) / BOT_THREADS;  // (the last warp runs past BOT_CAP when this does not divide: every use is guarded by p < len0)
 constexpr int BOT_WARPS = BOT_THREADS / 32;
 
 struct BotSmem {
