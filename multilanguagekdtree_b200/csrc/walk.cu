@@ -84,6 +84,12 @@ void walk_order_fork(Ctx* c) {
   c->order_pending = true;
 }
 
+// grids of at least this many waves of 28 CTAs per SM use the 72-register build of the production kernel
+#ifndef KDNB_W2_MINB28_WAVES
+#define KDNB_W2_MINB28_WAVES 2
+#endif
+constexpr uint32_t W2_MINB28_WAVES = KDNB_W2_MINB28_WAVES;
+
 static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
   const uint32_t grid = std::max<uint32_t>((end - begin + 31) / 32, 1u);
   const bool counts = (c->flags & KDNB_FLAG_WALK_COUNTS) != 0;
@@ -116,24 +122,29 @@ static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
     KDNB_LAUNCH(c, (walk2_kernel<true, false, true, 1>), grid, 32, 0, KDNB_WALK_ARGS);
   else if (counts)
     KDNB_LAUNCH(c, (walk2_kernel<false, true, true, 1>), grid, 32, 0, KDNB_WALK_ARGS);
-  else if (peer)
-    KDNB_LAUNCH(c, (walk2_kernel<false, false, true, 24>), grid, 32, 0, KDNB_WALK_ARGS);
   else {
-    static const int minb = [] {
-      const char* s = getenv("KDNB_WALK_MINB");  // profiling knob: CTAs per SM the register budget is sized for
-      return s ? atoi(s) : 24;
+    // Production kernel.  Register budget by grid size: 24 one-warp CTAs per SM = 80 registers (25 resident), or 28 per
+    // SM = 72 registers (40 bytes spilled; the 7296 bytes of shared memory are sized so that 28 fit).  More resident
+    // warps win once the grid is several waves deep — 2.046 -> 2.025 ms at N=1M (31251 CTAs), 20.15 -> 19.69 ms at
+    // N=10M — and lose on a grid of about one wave, where every CTA is resident either way and only the spills remain
+    // (0.289 -> 0.303 ms at 3907 CTAs, the 1/8 shard of N=1M); profiles/r02_ab_walk_unroll.txt, r02_ab_walk_minb_grid.txt.
+    // 32 per SM at 64 registers is slower at every size (profiles/r01_ab_walk_minb.txt); nor is the time a launch takes
+    // beyond its issue-slot work a matter of node / leaf load latency: prefetching the right child at push time and a
+    // leaf's particles at classification made every size ~1 % slower (profiles/r01_ab_walk_prefetch.txt).
+    static const int minb_env = [] {
+      const char* s = getenv("KDNB_WALK_MINB");  // profiling knob: 24 / 28 / 32 at every grid size
+      return s ? atoi(s) : 0;
     }();
-    // 24 one-warp CTAs per SM = 80 registers, no spills.  32 per SM at 64 registers is slower at every grid size, also
-    // where it would turn 1.1 waves into one (shard-sized grids: 0.394 against 0.374 ms at 3907 CTAs, 2.265 against
-    // 2.219 ms at 31251; profiles/r01_ab_walk_minb.txt) — the ~0.12 ms a launch takes beyond its issue-slot work is
-    // not a matter of waves; nor of node / leaf load latency: prefetching the right child at push time and a leaf's
-    // particles at classification made every size ~1 % slower (profiles/r01_ab_walk_prefetch.txt).
+    const int minb = minb_env ? minb_env : (grid >= W2_MINB28_WAVES * 28u * (uint32_t)c->num_sms ? 28 : 24);
 #ifdef KDNB_WALK_AB  // development experiment: KDNB_WALK_PAD=<bytes> of unused dynamic shared memory limits the CTAs per SM
     static const int pad = [] { const char* s = getenv("KDNB_WALK_PAD"); return s ? atoi(s) : 0; }();
 #else
     constexpr int pad = 0;
 #endif
-    if (minb == 32) KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 32>), grid, 32, 0, KDNB_WALK_ARGS);
+    if (peer) {
+      if (minb == 28) KDNB_LAUNCH(c, (walk2_kernel<false, false, true, 28>), grid, 32, 0, KDNB_WALK_ARGS);
+      else KDNB_LAUNCH(c, (walk2_kernel<false, false, true, 24>), grid, 32, 0, KDNB_WALK_ARGS);
+    } else if (minb == 32) KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 32>), grid, 32, 0, KDNB_WALK_ARGS);
     else if (minb == 28) KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 28>), grid, 32, 0, KDNB_WALK_ARGS);
     else KDNB_LAUNCH(c, (walk2_kernel<false, false, false, 24>), grid, 32, pad, KDNB_WALK_ARGS);
   }

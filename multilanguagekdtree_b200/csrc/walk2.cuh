@@ -43,11 +43,18 @@
 namespace kdnb {
 
 #ifndef KDNB_W2_STACK
-#define KDNB_W2_STACK 320
+#define KDNB_W2_STACK 304
 #endif
-constexpr int W2_STACK = KDNB_W2_STACK;  // soft capacity: batches shrink as the stack fills
+constexpr int W2_STACK = KDNB_W2_STACK;  // soft capacity: batches shrink as the stack fills (deepest use seen: 244 entries at N = 1M,
+                                         // 286 at 10M, tests/devtools/walk_model.c); 304 + the layout below = 7296 bytes for the
+                                         // production kernel, so that 28 CTAs fit an SM (walk.cu)
 constexpr int W2_SLACK = 32;   // depth-first tail when the stack is at capacity (tree depth <= 27 at 1e8 particles)
 constexpr int W2_LIST = 96;    // interaction-list capacity (appends come in groups of <= 32); multiple of 4
+
+#ifndef KDNB_W2_UNROLL
+#define KDNB_W2_UNROLL 2
+#endif
+constexpr int W2_UNROLL = KDNB_W2_UNROLL;  // list blocks per drain-loop iteration: 2 is 0.7 % faster than 1 at every size (profiles/r02_ab_walk_unroll.txt)
 
 // 1.875 = the e^2 coefficient of (1 - e)^(-3/2)
 __constant__ double W2_C2 = 1.875;
@@ -67,17 +74,35 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
-// four consecutive list entries: monopoles {cm, m} or leaf particles {p, m}, their lane masks, and (exact-math
-// contexts only) 1 = leaf particle.  128 bytes, so that the drain loop addresses everything off one base register.
-struct __align__(16) W2Blk {
+// four consecutive list entries: monopoles {cm, m} or leaf particles {p, m} and their lane masks; exact-math contexts
+// add 1 = leaf particle per entry.  A multiple of 16 bytes, so that the drain loop addresses everything off one base
+// register with 16-byte loads.
+template <bool EXACT>
+struct W2Blk;
+template <>
+struct __align__(16) W2Blk<false> {
+  double x[4], y[4], m[4];
+  uint32_t mask[4];
+};
+template <>
+struct __align__(16) W2Blk<true> {
   double x[4], y[4], m[4];
   uint32_t mask[4];
   uint32_t flag[4];
 };
-static_assert(sizeof(W2Blk) == 128, "W2Blk");
+static_assert(sizeof(W2Blk<false>) == 112 && sizeof(W2Blk<true>) == 128, "W2Blk");
 
-struct W2Smem {
-  W2Blk blk[W2_LIST / 4];
+template <bool COUNTS>
+struct W2CountSmem {
+  uint32_t mixmk[32];  // entry masks of the batch's mixed nodes (walk counters only)
+};
+template <>
+struct W2CountSmem<false> {};
+
+// shared memory of one warp: 7296 bytes in the production kernel (no flags, no counter scratch)
+template <bool EXACT, bool COUNTS>
+struct W2Smem : W2CountSmem<COUNTS> {
+  W2Blk<EXACT> blk[W2_LIST / 4];
   double lz[W2_LIST];  // z of the list entries (general inputs only)
   uint32_t snode[W2_STACK + W2_SLACK];
   uint32_t smask[W2_STACK + W2_SLACK];
@@ -85,9 +110,9 @@ struct W2Smem {
     Rec32 mix[32];  // {cx, cy, cz, size^2} of the batch's mixed nodes, compacted
     uint4 lq[32];   // {first slot, num_parts, lane mask, -} of the batch's leaves, compacted
   };
-  uint32_t mres[32];   // accept ballots of the batch's mixed nodes
-  uint32_t mixmk[32];  // their entry masks (walk counters only)
+  uint32_t mres[32];  // accept ballots of the batch's mixed nodes
 };
+static_assert(sizeof(W2Smem<false, false>) <= 7296, "production walk: 28 CTAs x (7296 + 1024 reserved) bytes per SM");
 
 // the reference's formulas (KDNB_FLAG_EXACT_MATH): node -m / (dist_sqr * dist) (array_kd_tree.rs:608), particle
 // -m / (dist*dist*dist) (array_particle.rs:72), IEEE sqrt and divide, unfused
@@ -123,8 +148,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #ifdef KDNB_WALK_AB
 __device__ int w2_dbg;  // development experiments: 1 = skip the drains, 2 = drain every list twice
 #endif
-template <bool EXACT, bool FLATZ>
-__device__ __forceinline__ void drain2(W2Smem& S, int cnt, int lane, double px, double py, double pz, double& ax,
+template <bool EXACT, bool COUNTS, bool FLATZ>
+__device__ __forceinline__ void drain2(W2Smem<EXACT, COUNTS>& S, int cnt, int lane, double px, double py, double pz, double& ax,
                                        double& ay, double& az) {
 #ifdef KDNB_WALK_CPASYNC
   cp_async_wait_all();
@@ -135,9 +160,9 @@ __device__ __forceinline__ void drain2(W2Smem& S, int cnt, int lane, double px, 
   if (dbg == 1) return;
   for (int rep = 0; rep < (dbg == 2 ? 2 : 1); ++rep)
 #endif
-  if (EXACT) {
+  if constexpr (EXACT) {
     for (int i = 0; i < cnt; ++i) {
-      const W2Blk& B = S.blk[i >> 2];
+      const W2Blk<EXACT>& B = S.blk[i >> 2];
       const int s = i & 3;
       interact_exact(B.x[s], B.y[s], S.lz[i], B.m[s], (B.mask[s] >> lane) & 1u, B.flag[s] != 0, px, py, pz, ax, ay, az);
     }
@@ -152,14 +177,15 @@ __device__ __forceinline__ void drain2(W2Smem& S, int cnt, int lane, double px, 
     const int nblk = (cnt + 3) >> 2;
     if (lane < 4 * nblk - cnt) {
       const int i = cnt + lane;
-      W2Blk& B = S.blk[i >> 2];
+      W2Blk<EXACT>& B = S.blk[i >> 2];
       B.x[i & 3] = B.y[i & 3] = B.m[i & 3] = 0.0;
       B.mask[i & 3] = 0u;
       if (!FLATZ) S.lz[i] = 0.0;
     }
     __syncwarp();
     const double* lz = S.lz;
-    for (const W2Blk *B = S.blk, *E = S.blk + nblk; B != E; ++B, lz += 4) {
+#pragma unroll W2_UNROLL
+    for (const W2Blk<EXACT>*B = S.blk, *E = S.blk + nblk; B != E; ++B, lz += 4) {
       double dx[4], dy[4], dz[4], d2[4], y[4], y2[4], ee[4], mq[4], q[4];
       const uint4 m4 = *reinterpret_cast<const uint4*>(B->mask);
       const uint32_t use[4] = {m4.x & lanebit, m4.y & lanebit, m4.z & lanebit, m4.w & lanebit};
@@ -217,21 +243,21 @@ __device__ __forceinline__ void drain2(W2Smem& S, int cnt, int lane, double px, 
 }
 
 // store list entry i
-template <bool EXACT, bool FLATZ>
-__device__ __forceinline__ void list_put(W2Smem& S, int i, double x, double y, double z, double m, uint32_t mask,
+template <bool EXACT, bool COUNTS, bool FLATZ>
+__device__ __forceinline__ void list_put(W2Smem<EXACT, COUNTS>& S, int i, double x, double y, double z, double m, uint32_t mask,
                                          uint32_t flag) {
-  W2Blk& B = S.blk[i >> 2];
+  W2Blk<EXACT>& B = S.blk[i >> 2];
   const int s = i & 3;
   B.x[s] = x, B.y[s] = y, B.m[s] = m;
   B.mask[s] = mask;
   if (!FLATZ) S.lz[i] = z;
-  if (EXACT) B.flag[s] = flag;
+  if constexpr (EXACT) B.flag[s] = flag;
 }
 
 enum : int { W2_NONE = 0, W2_FAR = 1, W2_NEAR = 2, W2_MIXED = 3, W2_LEAF = 4 };
 
 template <bool EXACT, bool COUNTS, bool PEER, bool FLATZ>
-__device__ __forceinline__ void walk2_body(W2Smem& S, const WNode* __restrict__ nodes,
+__device__ __forceinline__ void walk2_body(W2Smem<EXACT, COUNTS>& S, const WNode* __restrict__ nodes,
                                            const PosM* __restrict__ posm, double* __restrict__ acc_t,
                                            uint32_t slot_begin, uint32_t slot_end, double theta2,
                                            unsigned long long* __restrict__ wcounts, const P2P& p2p, int lshift,
@@ -340,7 +366,7 @@ __device__ __forceinline__ void walk2_body(W2Smem& S, const WNode* __restrict__ 
         Rec32 t;
         t.a = c.a, t.b = c.b, t.c = c.c, t.d = size2;
         S.mix[mrank] = t;
-        if (COUNTS) S.mixmk[mrank] = mk;
+        if constexpr (COUNTS) S.mixmk[mrank] = mk;
       }
       __syncwarp();
       const int nm = __popc(bal_mixed);
@@ -355,7 +381,7 @@ __device__ __forceinline__ void walk2_body(W2Smem& S, const WNode* __restrict__ 
         const bool accept = q.d < __dmul_rn(theta2, d2);  // :606
         const uint32_t b = __ballot_sync(0xffffffffu, accept);
         if (lane == 0) S.mres[k] = b;
-        if (COUNTS) {
+        if constexpr (COUNTS) {
           const bool in = (S.mixmk[k] >> lane) & 1u;
           cv += in;
           ca += in && accept;
@@ -376,11 +402,11 @@ __device__ __forceinline__ void walk2_body(W2Smem& S, const WNode* __restrict__ 
       if (bal) {
         const int add = __popc(bal);
         if (ln + add > W2_LIST) {
-          drain2<EXACT, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
+          drain2<EXACT, COUNTS, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
           work += (uint32_t)ln;
           ln = 0;
         }
-        if (mine) list_put<EXACT, FLATZ>(S, ln + __popc(bal & lt), c.a, c.b, c.c, c.d, amask, 0u);
+        if (mine) list_put<EXACT, COUNTS, FLATZ>(S, ln + __popc(bal & lt), c.a, c.b, c.c, c.d, amask, 0u);
         ln += add;
       }
     }
@@ -416,13 +442,13 @@ __device__ __forceinline__ void walk2_body(W2Smem& S, const WNode* __restrict__ 
         const int add = __popc(bal);
 #ifdef KDNB_WALK_CPASYNC
         if (ln + add > W2_LIST) {
-          drain2<EXACT, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
+          drain2<EXACT, COUNTS, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
           work += (uint32_t)ln;
           ln = 0;
         }
         if (valid) {
           const int i = ln + __popc(bal & lt);
-          W2Blk& B = S.blk[i >> 2];
+          W2Blk<EXACT>& B = S.blk[i >> 2];
           const int s = i & 3;
           const PosM* g = posm + j;
           cp_async8(&B.x[s], &g->x);
@@ -430,18 +456,18 @@ __device__ __forceinline__ void walk2_body(W2Smem& S, const WNode* __restrict__ 
           cp_async8(&B.m[s], &g->m);
           if (!FLATZ) cp_async8(&S.lz[i], &g->z);
           B.mask[s] = m;
-          if (EXACT) B.flag[s] = 1u;
+          if constexpr (EXACT) B.flag[s] = 1u;
         }
         ln += add;
 #else
         PosM qv;
         if (valid) qv = posm[j];
         if (ln + add > W2_LIST) {
-          drain2<EXACT, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
+          drain2<EXACT, COUNTS, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
           work += (uint32_t)ln;
           ln = 0;
         }
-        if (valid) list_put<EXACT, FLATZ>(S, ln + __popc(bal & lt), qv.x, qv.y, qv.z, qv.m, m, 1u);
+        if (valid) list_put<EXACT, COUNTS, FLATZ>(S, ln + __popc(bal & lt), qv.x, qv.y, qv.z, qv.m, m, 1u);
         ln += add;
 #endif
         if (COUNTS) {
@@ -454,7 +480,7 @@ __device__ __forceinline__ void walk2_body(W2Smem& S, const WNode* __restrict__ 
     }
     __syncwarp();
   }
-  drain2<EXACT, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
+  drain2<EXACT, COUNTS, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
   work += (uint32_t)ln;
   if (gcost && lane == 0 && warp_has_work) gcost[group] = work;
 
@@ -510,7 +536,7 @@ walk2_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, dou
              P2P p2p, const uint32_t* __restrict__ flat, int lshift, const uint32_t* __restrict__ gorder,
              uint32_t* __restrict__ gcost) {
   pdl_sync();
-  __shared__ W2Smem S;
+  __shared__ W2Smem<EXACT, COUNTS> S;
   if (!EXACT && !COUNTS && flat[3])
     walk2_body<EXACT, COUNTS, PEER, true>(S, nodes, posm, acc_t, slot_begin, slot_end, theta2, wcounts, p2p, lshift, gorder, gcost);
   else
