@@ -49,7 +49,14 @@ constexpr int W2_STACK = KDNB_W2_STACK;  // soft capacity: batches shrink as the
                                          // 286 at 10M, tests/devtools/walk_model.c); 304 + the layout below = 7296 bytes for the
                                          // production kernel, so that 28 CTAs fit an SM (walk.cu)
 constexpr int W2_SLACK = 32;   // depth-first tail when the stack is at capacity (tree depth <= 27 at 1e8 particles)
-constexpr int W2_LIST = 96;    // interaction-list capacity (appends come in groups of <= 32); multiple of 4
+#ifndef KDNB_W2_LIST
+#define KDNB_W2_LIST 96
+#endif
+#ifndef KDNB_W2_LIST_FLAT
+#define KDNB_W2_LIST_FLAT (KDNB_W2_LIST + KDNB_W2_LIST / 4)
+#endif
+constexpr int W2_LIST_FLAT = KDNB_W2_LIST_FLAT;  // capacity on planar inputs, where the z array is not needed: 120 (+0.x % over 96)
+constexpr int W2_LIST = KDNB_W2_LIST;    // interaction-list capacity (appends come in groups of <= 32); multiple of 4
 
 #ifndef KDNB_W2_UNROLL
 #define KDNB_W2_UNROLL 2
@@ -102,8 +109,13 @@ struct W2CountSmem<false> {};
 // shared memory of one warp: 7296 bytes in the production kernel (no flags, no counter scratch)
 template <bool EXACT, bool COUNTS>
 struct W2Smem : W2CountSmem<COUNTS> {
-  W2Blk<EXACT> blk[W2_LIST / 4];
-  double lz[W2_LIST];  // z of the list entries (general inputs only)
+  union {
+    struct {
+      W2Blk<EXACT> blk[W2_LIST / 4];
+      double lz[W2_LIST];  // z of the list entries (general inputs only)
+    };
+    W2Blk<EXACT> blkf[W2_LIST_FLAT / 4];  // planar inputs: no z, the same bytes hold a longer list
+  };
   uint32_t snode[W2_STACK + W2_SLACK];
   uint32_t smask[W2_STACK + W2_SLACK];
   union {
@@ -112,7 +124,7 @@ struct W2Smem : W2CountSmem<COUNTS> {
   };
   uint32_t mres[32];  // accept ballots of the batch's mixed nodes
 };
-static_assert(sizeof(W2Smem<false, false>) <= 7296, "production walk: 28 CTAs x (7296 + 1024 reserved) bytes per SM");
+static_assert(W2_LIST != 96 || W2_STACK != 304 || sizeof(W2Smem<false, false>) == 7296, "production walk: 28 CTAs x (7296 + 1024 reserved) bytes per SM");
 
 // the reference's formulas (KDNB_FLAG_EXACT_MATH): node -m / (dist_sqr * dist) (array_kd_tree.rs:608), particle
 // -m / (dist*dist*dist) (array_particle.rs:72), IEEE sqrt and divide, unfused
@@ -177,15 +189,16 @@ __device__ __forceinline__ void drain2(W2Smem<EXACT, COUNTS>& S, int cnt, int la
     const int nblk = (cnt + 3) >> 2;
     if (lane < 4 * nblk - cnt) {
       const int i = cnt + lane;
-      W2Blk<EXACT>& B = S.blk[i >> 2];
+      W2Blk<EXACT>& B = (FLATZ ? S.blkf : S.blk)[i >> 2];
       B.x[i & 3] = B.y[i & 3] = B.m[i & 3] = 0.0;
       B.mask[i & 3] = 0u;
       if (!FLATZ) S.lz[i] = 0.0;
     }
     __syncwarp();
     const double* lz = S.lz;
+    const W2Blk<EXACT>* B0 = FLATZ ? S.blkf : S.blk;
 #pragma unroll W2_UNROLL
-    for (const W2Blk<EXACT>*B = S.blk, *E = S.blk + nblk; B != E; ++B, lz += 4) {
+    for (const W2Blk<EXACT>*B = B0, *E = B0 + nblk; B != E; ++B, lz += 4) {
       double dx[4], dy[4], dz[4], d2[4], y[4], y2[4], ee[4], mq[4], q[4];
       const uint4 m4 = *reinterpret_cast<const uint4*>(B->mask);
       const uint32_t use[4] = {m4.x & lanebit, m4.y & lanebit, m4.z & lanebit, m4.w & lanebit};
@@ -246,7 +259,7 @@ __device__ __forceinline__ void drain2(W2Smem<EXACT, COUNTS>& S, int cnt, int la
 template <bool EXACT, bool COUNTS, bool FLATZ>
 __device__ __forceinline__ void list_put(W2Smem<EXACT, COUNTS>& S, int i, double x, double y, double z, double m, uint32_t mask,
                                          uint32_t flag) {
-  W2Blk<EXACT>& B = S.blk[i >> 2];
+  W2Blk<EXACT>& B = (FLATZ ? S.blkf : S.blk)[i >> 2];
   const int s = i & 3;
   B.x[s] = x, B.y[s] = y, B.m[s] = m;
   B.mask[s] = mask;
@@ -283,6 +296,7 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT, COUNTS>& S, const WNode
     lo[2] = hi[2] = me.z;
   }
   constexpr int ND = FLATZ ? 2 : 3;
+  constexpr int LCAP = FLATZ ? W2_LIST_FLAT : W2_LIST;  // interaction-list capacity
   // Box of the group as centre and half extent.  hs is the half extent INFLATED by 2^-46 of the box's scale: the
   // distance of a node to the box along one axis is then bounded from below by |c - mid| - hs and from above by
   // |c - mid| + hs whatever the roundings of mid, hs and the subtractions (each <= 2^-52 of that scale), also where
@@ -401,7 +415,7 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT, COUNTS>& S, const WNode
       const uint32_t bal = __ballot_sync(0xffffffffu, mine);
       if (bal) {
         const int add = __popc(bal);
-        if (ln + add > W2_LIST) {
+        if (ln + add > LCAP) {
           drain2<EXACT, COUNTS, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
           work += (uint32_t)ln;
           ln = 0;
@@ -441,14 +455,14 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT, COUNTS>& S, const WNode
         const uint32_t bal = __ballot_sync(0xffffffffu, valid);
         const int add = __popc(bal);
 #ifdef KDNB_WALK_CPASYNC
-        if (ln + add > W2_LIST) {
+        if (ln + add > LCAP) {
           drain2<EXACT, COUNTS, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
           work += (uint32_t)ln;
           ln = 0;
         }
         if (valid) {
           const int i = ln + __popc(bal & lt);
-          W2Blk<EXACT>& B = S.blk[i >> 2];
+          W2Blk<EXACT>& B = (FLATZ ? S.blkf : S.blk)[i >> 2];
           const int s = i & 3;
           const PosM* g = posm + j;
           cp_async8(&B.x[s], &g->x);
@@ -462,7 +476,7 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT, COUNTS>& S, const WNode
 #else
         PosM qv;
         if (valid) qv = posm[j];
-        if (ln + add > W2_LIST) {
+        if (ln + add > LCAP) {
           drain2<EXACT, COUNTS, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
           work += (uint32_t)ln;
           ln = 0;
