@@ -156,21 +156,22 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #endif
 
-// all lanes stream over the list; lane = particle
+// all lanes stream over the list; lane = particle.  Unless this is the group's last drain, only whole blocks of four
+// entries are evaluated and the 1-3 entries of an incomplete block move to the front of the list (returned count):
+// padding a block with masked-out entries costs a full interaction each, ~2 % of the list slots at 24 drains per group.
 #ifdef KDNB_WALK_AB
 __device__ int w2_dbg;  // development experiments: 1 = skip the drains, 2 = drain every list twice
 #endif
 template <bool EXACT, bool COUNTS, bool FLATZ>
-__device__ __forceinline__ void drain2(W2Smem<EXACT, COUNTS>& S, int cnt, int lane, double px, double py, double pz, double& ax,
-                                       double& ay, double& az) {
+__device__ __forceinline__ int drain2(W2Smem<EXACT, COUNTS>& S, int cnt, bool last, int lane, double px, double py, double pz,
+                                      double& ax, double& ay, double& az) {
 #ifdef KDNB_WALK_CPASYNC
   cp_async_wait_all();
 #endif
   __syncwarp();
 #ifdef KDNB_WALK_AB
   const int dbg = w2_dbg;
-  if (dbg == 1) return;
-  for (int rep = 0; rep < (dbg == 2 ? 2 : 1); ++rep)
+  if (dbg == 1) return 0;
 #endif
   if constexpr (EXACT) {
     for (int i = 0; i < cnt; ++i) {
@@ -186,6 +187,11 @@ __device__ __forceinline__ void drain2(W2Smem<EXACT, COUNTS>& S, int cnt, int la
     // contribution exactly -0 * d = no-op and also absorbs d2 == 0 (inf estimate).  (Predicating the accumulating FMAs
     // instead does not pay: ptxas turns a predicated DFMA into DFMA + two FSEL.)
     const uint32_t lanebit = 1u << lane;
+#ifdef KDNB_W2_NO_CARRY
+    last = true;
+#endif
+    const int rem = last ? 0 : (cnt & 3);  // entries carried over to the next drain
+    cnt -= rem;
     const int nblk = (cnt + 3) >> 2;
     if (lane < 4 * nblk - cnt) {
       const int i = cnt + lane;
@@ -197,6 +203,9 @@ __device__ __forceinline__ void drain2(W2Smem<EXACT, COUNTS>& S, int cnt, int la
     __syncwarp();
     const double* lz = S.lz;
     const W2Blk<EXACT>* B0 = FLATZ ? S.blkf : S.blk;
+#ifdef KDNB_WALK_AB
+    for (int rep = 0; rep < (dbg == 2 ? 2 : 1); ++rep, lz = S.lz)
+#endif
 #pragma unroll W2_UNROLL
     for (const W2Blk<EXACT>*B = B0, *E = B0 + nblk; B != E; ++B, lz += 4) {
       double dx[4], dy[4], dz[4], d2[4], y[4], y2[4], ee[4], mq[4], q[4];
@@ -251,8 +260,21 @@ __device__ __forceinline__ void drain2(W2Smem<EXACT, COUNTS>& S, int cnt, int la
         if (!FLATZ) az = fma(mq[j], dz[j], az);
       }
     }
+    if (rem) {  // (cnt is a multiple of 4 here, and > 0: a drain that is not the last one is triggered by a full list)
+      __syncwarp();
+      if (lane < rem) {
+        W2Blk<EXACT>* Bw = FLATZ ? S.blkf : S.blk;
+        const W2Blk<EXACT>& Bs = Bw[cnt >> 2];
+        Bw[0].x[lane] = Bs.x[lane], Bw[0].y[lane] = Bs.y[lane], Bw[0].m[lane] = Bs.m[lane];
+        Bw[0].mask[lane] = Bs.mask[lane];
+        if (!FLATZ) S.lz[lane] = S.lz[cnt + lane];
+      }
+    }
+    __syncwarp();
+    return rem;
   }
   __syncwarp();
+  return 0;
 }
 
 // store list entry i
@@ -416,9 +438,9 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT, COUNTS>& S, const WNode
       if (bal) {
         const int add = __popc(bal);
         if (ln + add > LCAP) {
-          drain2<EXACT, COUNTS, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
-          work += (uint32_t)ln;
-          ln = 0;
+          const int left = drain2<EXACT, COUNTS, FLATZ>(S, ln, false, lane, px, py, pz, ax, ay, az);
+          work += (uint32_t)(ln - left);
+          ln = left;
         }
         if (mine) list_put<EXACT, COUNTS, FLATZ>(S, ln + __popc(bal & lt), c.a, c.b, c.c, c.d, amask, 0u);
         ln += add;
@@ -456,9 +478,9 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT, COUNTS>& S, const WNode
         const int add = __popc(bal);
 #ifdef KDNB_WALK_CPASYNC
         if (ln + add > LCAP) {
-          drain2<EXACT, COUNTS, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
-          work += (uint32_t)ln;
-          ln = 0;
+          const int left = drain2<EXACT, COUNTS, FLATZ>(S, ln, false, lane, px, py, pz, ax, ay, az);
+          work += (uint32_t)(ln - left);
+          ln = left;
         }
         if (valid) {
           const int i = ln + __popc(bal & lt);
@@ -477,9 +499,9 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT, COUNTS>& S, const WNode
         PosM qv;
         if (valid) qv = posm[j];
         if (ln + add > LCAP) {
-          drain2<EXACT, COUNTS, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
-          work += (uint32_t)ln;
-          ln = 0;
+          const int left = drain2<EXACT, COUNTS, FLATZ>(S, ln, false, lane, px, py, pz, ax, ay, az);
+          work += (uint32_t)(ln - left);
+          ln = left;
         }
         if (valid) list_put<EXACT, COUNTS, FLATZ>(S, ln + __popc(bal & lt), qv.x, qv.y, qv.z, qv.m, m, 1u);
         ln += add;
@@ -494,7 +516,7 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT, COUNTS>& S, const WNode
     }
     __syncwarp();
   }
-  drain2<EXACT, COUNTS, FLATZ>(S, ln, lane, px, py, pz, ax, ay, az);
+  drain2<EXACT, COUNTS, FLATZ>(S, ln, true, lane, px, py, pz, ax, ay, az);
   work += (uint32_t)ln;
   if (gcost && lane == 0 && warp_has_work) gcost[group] = work;
 
