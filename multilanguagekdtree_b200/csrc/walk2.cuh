@@ -3,8 +3,8 @@
 // theta-criterion force walk, calc_accel / accel_recur of the reference
 // (Parallel/RustVersion/src/array_kd_tree.rs:585-621) with calc_pp_accel (array_particle.rs:67-76) in the leaves.
 //
-// One warp (= one CTA, 24 CTAs per SM) owns 32 consecutive TREE-ORDERED particles (a compact patch of ~4 leaves), one
-// per lane, and keeps a shared-memory stack of frontier entries (node, lane mask).  Per round it pops up to 32
+// One warp (= one CTA, 24 or 28 CTAs per SM: walk.cu) owns 32 consecutive TREE-ORDERED particles (a compact patch of
+// ~4 leaves), one per lane, and keeps a shared-memory stack of frontier entries (node, lane mask).  Per round it pops up to 32
 // entries and classifies them ONE NODE PER LANE against the bounding box of the 32 particles:
 //   far   : size^2 <  theta^2 * dmin^2 * (1 - 1e-9)  -> every particle in the entry's mask accepts the node
 //   near  : size^2 >= theta^2 * dmax^2 * (1 + 1e-9)  -> every particle opens it
@@ -29,8 +29,9 @@
 // reproduce the measured time), and every change is judged by the instructions it removes.
 //
 // Forces are not evaluated during the traversal: the interaction list is drained by a branch-free loop over blocks of
-// four interactions (W2Blk: one base register, seven 16-byte broadcast loads), 13 FP64 + 6 other instructions per
-// interaction on planar inputs.  When every z coordinate is +-0 and every mass is > 0 (flat[3], sort.cu: sort_prep —
+// four interactions (W2Blk: one base register, seven 16-byte broadcast loads), two blocks per iteration, 13 FP64 + 6.3
+// other instructions per interaction on planar inputs; an incomplete block waits for the next drain instead of being
+// padded.  When every z coordinate is +-0 and every mass is > 0 (flat[3], sort.cu: sort_prep —
 // the reference's own initial conditions, circular_orbits, array_particle.rs:19-44, are planar for ever) all
 // centre-of-mass z are +-0 too, dz is exactly 0 in every interaction and every test, and the z terms are skipped: the
 // results are bit-identical to the general path, az stays +0.
