@@ -310,6 +310,18 @@ def test_walk_production_kernel_equals_counted_kernel(orc, case):
         assert np.all(fast[:, 2] == 0.0)
 
 
+@pytest.mark.parametrize("shape", ["ring", "cube"])
+def test_walk_production_kernel_on_a_grid_of_several_waves(orc, shape):
+    """From two waves of 28 x (number of SMs) one-warp CTAs the production walk is launched in its 72-register build
+    (walk.cu: launch_walk2) — sizes the other walk tests never reach.  Same source, other register allocation: it must
+    still equal the counting variant bit for bit, planar (z terms skipped, 120-entry list) and general."""
+    parts = orc.circular_orbits(320_000, seed=91) if shape == "ring" else cube(300_000, seed=92, equal_mass=False)
+    fast = _acc(parts)
+    counted = _acc(parts, flags=kd.FLAG_WALK_COUNTS)
+    assert np.array_equal(fast, counted)
+    assert np.all(np.isfinite(fast))
+
+
 @pytest.mark.parametrize("mp", [4, 7])
 @pytest.mark.parametrize("shape", ["ring", "cube"])
 def test_walk_other_max_parts(orc, mp, shape):
