@@ -130,6 +130,7 @@ static void free_all(Ctx* c) {
   fr(c->tmp3);
   fr(c->gcost);
   fr(c->gorder);
+  fr(c->wseed);
   c->gcost_n = 0;
 }
 
@@ -334,6 +335,7 @@ static int plan(Ctx* c, uint64_t n) {
     if (!rc) rc = dev_alloc(c, &c->tmp3, 4 * n);
     if (!rc) rc = dev_alloc(c, &c->gcost, n / 32 + 2);
     if (!rc) rc = dev_alloc(c, &c->gorder, n / 32 + 2);
+    if (!rc) rc = dev_alloc(c, &c->wseed, 64);
     if (rc) {
       const std::string why = c->err;
       free_all(c);
@@ -350,6 +352,29 @@ static int plan(Ctx* c, uint64_t n) {
     c->planned_n = n;
   }
   c->acc_stride = 3 * padded_slots(c->cap);
+  {
+    // The top of the tree is the same descent for every group of the walk: node indices of depths 0-5 in heap order
+    // (closed form: the left child follows its parent, the right child follows the left subtree), usable when every
+    // node of depths 0-4 is internal.  Identical on every rank, whatever part of the tree it builds.
+    uint32_t node[64];
+    uint64_t len[64];
+    memset(node, 0, sizeof node);
+    memset(len, 0, sizeof len);
+    node[1] = 0, len[1] = n;
+    bool ok = true;
+    for (int h = 1; h < 32 && ok; ++h) {
+      if (len[h] <= c->mp) ok = false;
+      const uint64_t half = len[h] / 2;
+      node[2 * h] = node[h] + 1, len[2 * h] = half;
+      node[2 * h + 1] = node[h] + 1 + (uint32_t)subtree_nodes(half, c->mp, c->layout), len[2 * h + 1] = len[h] - half;
+    }
+    static const bool off = [] { const char* s = getenv("KDNB_WALK_SEED"); return s && atoi(s) == 0; }();
+    c->wseed_ok = ok && !off;
+    if (c->wseed_ok) {
+      KDNB_CUDA_TRY(c, cudaMemcpyAsync(c->wseed, node + 1, 63 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+      KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // (node[] is a stack array)
+    }
+  }
   if (c->world > 1) {
     c->shard_slots = shard_slots_for(n, c->world);
     if (grow || !c->p2p_ready) {

@@ -114,7 +114,7 @@ static void launch_walk2(Ctx* c, uint32_t begin, uint32_t end) {
     c->gcost_end = end;
   }
   c->order_pending = false;
-#define KDNB_WALK_ARGS c->nodes, c->posm, c->acc_t, begin, end, c->theta2, c->wcounts, pp, c->flat, lshift, gorder, gcost
+#define KDNB_WALK_ARGS c->nodes, c->posm, c->acc_t, begin, end, c->theta2, c->wcounts, pp, c->flat, lshift, gorder, gcost, (c->wseed_ok ? c->wseed : nullptr)
   const bool peer = pp.world > 1;
   if (exact && counts)
     KDNB_LAUNCH(c, (walk2_kernel<true, true, true, 1>), grid, 32, 0, KDNB_WALK_ARGS);

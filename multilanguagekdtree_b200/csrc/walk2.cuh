@@ -297,7 +297,8 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT, COUNTS>& S, const WNode
                                            const PosM* __restrict__ posm, double* __restrict__ acc_t,
                                            uint32_t slot_begin, uint32_t slot_end, double theta2,
                                            unsigned long long* __restrict__ wcounts, const P2P& p2p, int lshift,
-                                           const uint32_t* __restrict__ gorder, uint32_t* __restrict__ gcost) {
+                                           const uint32_t* __restrict__ gorder, uint32_t* __restrict__ gcost,
+                                           const uint32_t* __restrict__ seed) {
   const int lane = threadIdx.x;
   const uint32_t lt = (1u << lane) - 1u;
   // CTA -> group of 32 tree slots: in launch order, or heaviest first by the previous step's work (walk.cu)
@@ -346,6 +347,32 @@ __device__ __forceinline__ void walk2_body(W2Smem<EXACT, COUNTS>& S, const WNode
 
   int ln = 0;
   int sp = warp_has_work ? 1 : 0;
+  // ---- the common descent.  Every group would start with five nearly empty batches (1, 2, 4, 8, 16 nodes) that open
+  // the same top of the tree.  seed[] (plan(): node indices of depths 0-5 in heap order, depths 0-4 all internal):
+  // lanes 0-30 test the 31 nodes of depths 0-4 against the group's box; if every particle opens all of them (the rule
+  // with theta < 1), the traversal starts from the 32 nodes of depth 5.  Otherwise it starts at the root as before.
+  if (seed != nullptr && warp_has_work) {
+    const uint32_t nd = seed[lane];  // (lane 31 reads the first node of depth 5 and is not part of the vote)
+    const Rec32* rec = reinterpret_cast<const Rec32*>(nodes + nd);
+    const int4 info = __ldg(reinterpret_cast<const int4*>(rec + 1));
+    const Rec32 c = rec[0];
+    const double size2 = __hiloint2double(info.y, info.x);
+    const double cc[3] = {c.a, c.b, c.c};
+    double dmax2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      const double df = fabs(cc[k] - mid[k]) + hs[k];
+      dmax2 = fma(df, df, dmax2);
+    }
+    const bool opened = lane == 31 || size2 >= tnear * dmax2;
+    if (__all_sync(0xffffffffu, opened)) {
+      S.snode[lane] = seed[31 + lane];
+      S.smask[lane] = __ballot_sync(0xffffffffu, valid_p);
+      sp = 32;
+      if (COUNTS && valid_p) cv += 31;  // every particle tested (and opened) the 31 nodes above
+      __syncwarp();
+    }
+  }
   while (sp > 0) {
     // ---- pop a batch: lane l takes entry sp+l after the pop (order inside a batch is irrelevant); lanes beyond the
     // batch re-read its first entry (no divergence, no dead values) and drop out after the classification
@@ -571,13 +598,13 @@ __global__ void __launch_bounds__(32, MINB)
 walk2_kernel(const WNode* __restrict__ nodes, const PosM* __restrict__ posm, double* __restrict__ acc_t,
              uint32_t slot_begin, uint32_t slot_end, double theta2, unsigned long long* __restrict__ wcounts,
              P2P p2p, const uint32_t* __restrict__ flat, int lshift, const uint32_t* __restrict__ gorder,
-             uint32_t* __restrict__ gcost) {
+             uint32_t* __restrict__ gcost, const uint32_t* __restrict__ seed) {
   pdl_sync();
   __shared__ W2Smem<EXACT, COUNTS> S;
   if (!EXACT && !COUNTS && flat[3])
-    walk2_body<EXACT, COUNTS, PEER, true>(S, nodes, posm, acc_t, slot_begin, slot_end, theta2, wcounts, p2p, lshift, gorder, gcost);
+    walk2_body<EXACT, COUNTS, PEER, true>(S, nodes, posm, acc_t, slot_begin, slot_end, theta2, wcounts, p2p, lshift, gorder, gcost, seed);
   else
-    walk2_body<EXACT, COUNTS, PEER, false>(S, nodes, posm, acc_t, slot_begin, slot_end, theta2, wcounts, p2p, lshift, gorder, gcost);
+    walk2_body<EXACT, COUNTS, PEER, false>(S, nodes, posm, acc_t, slot_begin, slot_end, theta2, wcounts, p2p, lshift, gorder, gcost, seed);
 }
 
 // Heaviest-first launch order for the next walk (one CTA): gorder = the groups sorted by descending gcost, by a
