@@ -56,7 +56,8 @@ constexpr int W2_SLACK = 32;   // depth-first tail when the stack is at capacity
 #ifndef KDNB_W2_LIST_FLAT
 #define KDNB_W2_LIST_FLAT (KDNB_W2_LIST + KDNB_W2_LIST / 4)
 #endif
-constexpr int W2_LIST_FLAT = KDNB_W2_LIST_FLAT;  // capacity on planar inputs, where the z array is not needed: 120 (+0.x % over 96)
+constexpr int W2_LIST_FLAT = KDNB_W2_LIST_FLAT;  // capacity on planar inputs, where the z array's bytes are free: 120 (-0.3 % against 96, +2 % at 64:
+                                                 // profiles/r02_ab_walk_list_capacity.txt)
 constexpr int W2_LIST = KDNB_W2_LIST;    // interaction-list capacity (appends come in groups of <= 32); multiple of 4
 
 #ifndef KDNB_W2_UNROLL
