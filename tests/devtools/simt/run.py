@@ -3,7 +3,8 @@ the CPU, one fiber per CUDA thread (see cuda_runtime.h in this directory) — e.
 
     python tests/devtools/simt/run.py -k "build_padded or walk_ring" -x -q
 
-Everything after the script name goes to pytest.  Sizes above ~20k particles take minutes.  This never touches the
+Everything after the script name goes to pytest.  Sizes above ~20k particles take minutes (deselect
+test_walk_production_kernel_on_a_grid_of_several_waves: 300k particles).  This never touches the
 product: it re-points the ctypes loader of THIS process at the emulated library."""
 import os
 import sys
@@ -29,12 +30,15 @@ _site = os.path.join(HERE, "_build", "site")
 _libdir = os.path.join(HERE, "_build", "libdir")
 os.makedirs(_site, exist_ok=True)
 os.makedirs(_libdir, exist_ok=True)
-with open(os.path.join(_site, "sitecustomize.py"), "w") as f:
+# (written under process-private names and renamed into place: several of these runners may start at once, pytest -n)
+_tmp = os.path.join(_site, "sitecustomize.py.%d" % os.getpid())
+with open(_tmp, "w") as f:
     f.write("import sys\nsys.path.insert(0, %r)\nfrom multilanguagekdtree_b200 import _lib\n_lib.LIB_PATH = %r\n" % (ROOT, lib))
+os.replace(_tmp, os.path.join(_site, "sitecustomize.py"))
 _link = os.path.join(_libdir, "libkdnb.so")
-if os.path.islink(_link) or os.path.exists(_link):
-    os.remove(_link)
-os.symlink(lib, _link)
+_tmp = _link + ".%d" % os.getpid()
+os.symlink(lib, _tmp)
+os.replace(_tmp, _link)
 os.environ["PYTHONPATH"] = _site + os.pathsep + os.environ.get("PYTHONPATH", "")
 os.environ["LD_LIBRARY_PATH"] = _libdir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", "")
 import pytest  # noqa: E402
