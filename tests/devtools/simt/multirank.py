@@ -29,8 +29,10 @@ lib = simt_build.build()
 fake = os.path.join(HERE, "_build", "libnccl.so.2")
 src = os.path.join(HERE, "fake_nccl.cpp")
 if True:  # always rebuilt from fake_nccl.cpp (a second of g++): a stale or foreign binary of that name must never be loaded
-    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-Wl,-soname,libnccl.so.2", "-o", fake, src, "-lpthread"],
+    tmp = fake + ".%d" % os.getpid()  # (renamed into place: several of these processes may start at once, pytest -n)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-Wl,-soname,libnccl.so.2", "-o", tmp, src, "-lpthread"],
                    check=True)
+    os.replace(tmp, fake)
 C.CDLL(fake, mode=C.RTLD_GLOBAL)                     # dlopen("libnccl.so.2") inside the library now finds this one
 from multilanguagekdtree_b200 import _lib  # noqa: E402
 
