@@ -110,6 +110,7 @@ struct Ctx {
   uint64_t gcost_n = 0;        // particle count / shard the recorded work belongs to (0: none)
   uint32_t* wseed = nullptr;   // [64] node indices of tree depths 0-5 in heap order (walk2.cuh: the groups' common descent), plan()
   bool wseed_ok = false;       // every node of depths 0-4 is internal for this (n, max_parts)
+  uint64_t wseed_n = ~0ull;    // particle count the table was computed for
   uint32_t gcost_begin = 0, gcost_end = 0;
   bool tree_valid = false, acc_valid = false, map_valid = false;
   bool bottom_attr_set = false;  // build_bottom's dynamic shared memory limit raised on this context's device

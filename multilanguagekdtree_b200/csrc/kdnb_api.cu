@@ -131,6 +131,7 @@ static void free_all(Ctx* c) {
   fr(c->gcost);
   fr(c->gorder);
   fr(c->wseed);
+  c->wseed_n = ~0ull;
   c->gcost_n = 0;
 }
 
@@ -352,7 +353,7 @@ static int plan(Ctx* c, uint64_t n) {
     c->planned_n = n;
   }
   c->acc_stride = 3 * padded_slots(c->cap);
-  {
+  if (grow || c->wseed_n != n) {
     // The top of the tree is the same descent for every group of the walk: node indices of depths 0-5 in heap order
     // (closed form: the left child follows its parent, the right child follows the left subtree), usable when every
     // node of depths 0-4 is internal.  Identical on every rank, whatever part of the tree it builds.
@@ -374,6 +375,7 @@ static int plan(Ctx* c, uint64_t n) {
       KDNB_CUDA_TRY(c, cudaMemcpyAsync(c->wseed, node + 1, 63 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
       KDNB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // (node[] is a stack array)
     }
+    c->wseed_n = n;
   }
   if (c->world > 1) {
     c->shard_slots = shard_slots_for(n, c->world);

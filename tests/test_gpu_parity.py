@@ -260,6 +260,24 @@ def test_walk_ring_acc_and_decisions(orc, n):
     assert rel_err(acc, oacc).max() <= ACC_RTOL
 
 
+def test_one_context_walks_different_particle_counts(orc):
+    """Per-size host state of the walk (the closed-form node indices of the top of the tree that seed the traversal,
+    kdnb_api.cu: plan) must follow the particle count when one context is loaded with another set: growing, shrinking to
+    a size without that seed (a tree shallower than five internal levels), and back."""
+    with kd.KDTreeSim(flags=kd.FLAG_WALK_COUNTS) as sim:
+        for n in (3000, 7000, 60, 3000, 1200):
+            parts = orc.circular_orbits(n, seed=n + 11)
+            sim.upload(parts)
+            sim.build_tree()
+            sim.calc_accel()
+            acc, cnt = sim.accel(), sim.walk_counts()
+            gnodes, gidx = sim.tree()
+            oacc, ocnt = orc.calc_accel_all(parts, to_oracle_nodes(orc, gnodes, gidx, 8), counts=True)
+            for k, f in enumerate(("node_visits", "accepts", "leaf_visits", "pp")):
+                assert np.array_equal(cnt[:, k], ocnt[f]), (n, f)
+            assert rel_err(acc, oacc).max() <= ACC_RTOL, n
+
+
 def test_walk_ring_self_gravity_visible(orc):
     """SURVEY.md §7 hard part 4: the central mass (m=1 vs 1e-14) hides ring-ring errors at the 1e-12 level.
     Drop the central body so that every force IS ring self-gravity and opening mistakes would show."""

@@ -16,7 +16,7 @@ SELECTION = ("test_build_padded_ring_bit_exact and (2049 or 12293) or test_build
              "or test_build_3d_and_ties_bit_exact and 3000 or test_walk_ring_acc_and_decisions and 5000 "
              "or test_walk_production_kernel_equals_counted_kernel and cube_unequal or test_walk_equal_mass_cube and 0.5 "
              "or test_kick_drift_bit_exact or test_simple_sim_trajectory and 1000-100 or test_quickstat_small_test_kat_gpu "
-             "or test_degenerate_geometries_tree_and_walk and grid and 7")
+             "or test_degenerate_geometries_tree_and_walk and grid and 7 or test_one_context_walks_different_particle_counts")
 
 
 @pytest.mark.timeout(900)
