@@ -154,12 +154,18 @@ def one(seed: int, max_n: int) -> str:
         sim.calc_accel()
         acc2 = sim.accel()
         assert np.array_equal(T.bits(acc2), T.bits(acc)), "production walk != counting walk"
-        # short trajectory
+        # short trajectory.  Where the first kick throws the whole set astronomically far (coincident particles whose
+        # centre of mass is one ulp off: |a| ~ 1e31), the next step depends on whether the new positions coincide to
+        # the last bit — the summation order decides between finite and NaN, in the reference as well — so only one
+        # step is comparable.
+        fin = np.isfinite(acc).all(axis=1)
+        blown = bool(fin.any()) and float(np.abs(acc[fin]).max()) * 1e-6 > 1e3 * max(float(np.abs(parts["p"]).max()), 1e-300)
+        steps = 1 if blown else 3
         sim.upload(parts)
-        sim.simple_sim(1e-3, 3)
+        sim.simple_sim(1e-3, steps)
         out = sim.download()
     ref = parts.copy()
-    orc.simple_sim(ref, 1e-3, 3, max_parts=mp, theta=theta, layout=olayout, order=okd.ORDER_CANONICAL)
+    orc.simple_sim(ref, 1e-3, steps, max_parts=mp, theta=theta, layout=olayout, order=okd.ORDER_CANONICAL)
     for f in ("p", "v"):
         ok, why = close_on_the_global_scale(out[f], ref[f], 1e-11)
         assert ok, f"trajectory {f}: {why}"
